@@ -46,6 +46,7 @@ struct ah_ctx {
     void *hPinned = nullptr;  // pinned bounce buffer for the per-k outputs
     size_t hPinnedCap = 0;
     std::vector<double> hPadD, hPadW;
+    unsigned long long *hCounts = nullptr;  // pinned, 64 entries: per-block hand-over counts of the last call
 };
 
 namespace {
@@ -254,7 +255,8 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
 
     float ms_main = 0.f, ms_all = 0.f;
     int64_t n_full = 0;
-    int nbuf = 0;
+    int nbuf = 0, n_count_reads = 0;
+    for (int q = 0; q < 64; ++q) ctx->hCounts[q] = 0;
     for (int64_t c0 = 0; c0 < cnt; c0 += chunk, ++nbuf) {
         const int64_t cc = std::min(chunk, cnt - c0);
         const int slot = nbuf & 1;
@@ -283,29 +285,28 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "fast kernel launch");
             ctx->stats.launches += 1;
             AH_CUDA(cudaEventRecord(ctx->ev[3], st));
-            unsigned long long hcount[2] = {0, 0};
-            AH_CUDA(cudaMemcpyAsync(hcount, dcount, 16, cudaMemcpyDeviceToHost, st));
-            AH_CUDA(cudaStreamSynchronize(st));
-            const int64_t nf = (int64_t)hcount[0];
-            if (nf > 0) {
-                const int grid = (int)std::min<int64_t>(nf, (int64_t)ctx->sm_count * 4);
+            {
+                // the hand-over list is consumed straight from device memory; a few hundred CTAs cover the
+                // ~1 % of eigenpairs that take a Remedy / double-double branch
+                const int grid = (int)std::min<int64_t>(cc, (int64_t)ctx->sm_count * 4);
                 switch (L.kind) {
-                    case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, nf); break;
-                    case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, nf); break;
-                    default: k_full<KIND_HALF, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, nf); break;
+                    case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, 0, dcount); break;
+                    case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, 0, dcount); break;
+                    default: k_full<KIND_HALF, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, 0, dcount); break;
                 }
                 AH_CUDA(cudaGetLastError());
                 ctx->stats.launches += 1;
             }
-            n_full += nf;
+            AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[nbuf & 63], dcount, 8, cudaMemcpyDeviceToHost, st));
+            n_count_reads = std::min(nbuf + 1, 64);
             AH_CUDA(cudaEventRecord(ctx->ev[4], st));
         } else {
             AH_CUDA(cudaEventRecord(ctx->ev[3], st));
             const int grid = (int)std::min<int64_t>(cc, (int64_t)ctx->sm_count * 4);
             switch (L.kind) {
-                case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, st>>>(P, Oc, nullptr, kb, cc); break;
-                case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, st>>>(P, Oc, nullptr, kb, cc); break;
-                default: k_full<KIND_HALF, 256><<<grid, 256, 0, st>>>(P, Oc, nullptr, kb, cc); break;
+                case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, st>>>(P, Oc, nullptr, kb, cc, nullptr); break;
+                case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, st>>>(P, Oc, nullptr, kb, cc, nullptr); break;
+                default: k_full<KIND_HALF, 256><<<grid, 256, 0, st>>>(P, Oc, nullptr, kb, cc, nullptr); break;
             }
             AH_CUDA(cudaGetLastError());
             ctx->stats.launches += 1;
@@ -374,6 +375,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     ctx->stats.d2h_ms = td;
     ctx->stats.kernel_ms = ms_all;
     ctx->stats.main_kernel_ms = ms_main;
+    for (int q = 0; q < n_count_reads; ++q) n_full += (int64_t)ctx->hCounts[q];
     ctx->stats.n_full = n_full;
     ctx->stats.n_fast = cnt - n_full;
     return AH_OK;
@@ -456,6 +458,7 @@ int ah_create(ah_ctx **pctx, int device) {
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (auto &ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     for (auto &ev : ctx->ev_stage) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaMallocHost((void **)&ctx->hCounts, 64 * sizeof(unsigned long long)) == cudaSuccess;
     if (ok) ok = ah::configure_fast_kernels() == 0;
     if (!ok) {
         cudaError_t le = cudaGetLastError();
@@ -474,6 +477,7 @@ void ah_destroy(ah_ctx *ctx) {
                       &ctx->dCount, &ctx->dStage[0], &ctx->dStage[1]})
         if (b->p) cudaFree(b->p);
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+    if (ctx->hCounts) cudaFreeHost(ctx->hCounts);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -265,7 +265,7 @@ k_fast(Problem P, Outputs O, int64_t kbase, int64_t cnt, int64_t *__restrict__ d
                     const double nu = S.right;
                     const int64_t ii = S.i - 1;
                     const double Knu = __ddiv_rn(S.nu1, fabs(nu));
-                    bool bail = isinf(nu);
+                    bool bail = !isfinite(nu);
                     if (KIND == KIND_HALF) bail = bail || !(Knu < P.tau[2]);
                     else bail = bail || (Knu > P.tau[2]);
                     double mu = 0.0, lambda = 0.0;
