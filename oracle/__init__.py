@@ -9,7 +9,7 @@ drivers (sorting, deflation, back-permutation: arrowhead3.jl:567-657, arrowhead4
 arrowhead6.jl:526-661, arrowhead7.jl:10-36).  The reference is Julia and cannot run in this image;
 parity is pinned by the reference's own known-answer vectors (tests/golden/, tests/test_oracle_golden.py).
 """
-from .lib import OracleLib, get_lib, build  # noqa: F401
+from .lib import OracleLib, get_lib, get_lib_hi, build  # noqa: F401
 from .drivers import (  # noqa: F401
     eigen_symarrow,
     eigen_symdpr1,

@@ -46,6 +46,16 @@
 
 #define AH_EPS 2.220446049250313e-16
 
+/* Accumulator type of every O(N) sum.  Default build: double, i.e. exactly the reference's rounding
+ * sequence.  -DAH_ORACLE_HI: x87 long double (64-bit significand) -- the same algorithm with (nearly)
+ * exactly rounded sums, used by the tests to tell the reference's own summation noise (which the
+ * algorithm amplifies by up to Knu <= tolnu = 1e3) apart from an error of the implementation under test. */
+#ifdef AH_ORACLE_HI
+typedef long double acc_t;
+#else
+typedef double acc_t;
+#endif
+
 #define AH_ST_OK 0
 #define AH_ST_NU_INF 1          /* |nu|==Inf deflation branch taken (arrowhead3.jl:451-455) */
 #define AH_ST_NEEDS_BIGFLOAT 2  /* reference would switch to BigFloat (Qout 50 / 100) */
@@ -77,6 +87,11 @@ static inline int jl_isequal(double a, double b) {
 
 /* Julia `sum` over an array: pairwise above 1024 elements, sequential inside a block. */
 static double jl_pairwise_sum(const double *x, int64_t lo, int64_t hi /* inclusive */) {
+#ifdef AH_ORACLE_HI
+    acc_t v = 0.0;
+    for (int64_t i = lo; i <= hi; ++i) v += x[i];
+    return (double)v;
+#endif
     if (hi < lo) return 0.0;
     if (lo == hi) return x[lo];
     if (hi - lo < 1024) {
@@ -174,7 +189,7 @@ static double bisect_arrow(const double *D, const double *z, double a, int64_t n
     for (int64_t k = 0; k < n; ++k) zsq[k] = zsq[k] * zsq[k];
     int32_t cnt = 0;
     while ((right - left) > 2.0 * AH_EPS * jl_max(fabs(left), fabs(right))) {
-        double F = 0.0;
+        acc_t F = 0.0;
         for (int64_t k = 0; k < n; ++k) F += zsq[k] / (D[k] - middle);
         F = a - middle - F;
         if (F > 0.0) left = middle; else right = middle;
@@ -195,7 +210,7 @@ static double bisect_dpr1(const double *D, const double *u, double r, int64_t n,
         if (d > mx1) { mx2 = mx1; mx1 = d; } else if (d > mx2) mx2 = d;
         if (d < mn1) { mn2 = mn1; mn1 = d; } else if (d < mn2) mn2 = d;
     }
-    double uu = 0.0;
+    acc_t uu = 0.0;
     for (int64_t k = 0; k < n; ++k) uu += u[k] * u[k];
     double left, right;
     if (r > 0.0) {
@@ -210,7 +225,7 @@ static double bisect_dpr1(const double *D, const double *u, double r, int64_t n,
     double sr = jl_sign(r);
     int32_t cnt = 0;
     while ((right - left) > 2.0 * AH_EPS * jl_max(fabs(left), fabs(right))) {
-        double F = 0.0;
+        acc_t F = 0.0;
         for (int64_t k = 0; k < n; ++k) F = F + usq[k] / (D[k] - middle);
         F = 1.0 + r * F;
         if (sr * F < 0.0) left = middle; else right = middle;
@@ -260,7 +275,7 @@ static void arrow_inv_shift_index(int64_t N, const double *D, const double *z, d
         Bz[k - 1] = -z[k] * Bd[k - 1] * wz;
     }
     double as = a - sigma;
-    double P = 0.0, Q = 0.0;
+    acc_t P = 0.0, Q = 0.0;
     *Qout = 0;
     for (int64_t k = 0; k < ii; ++k) {
         if (Bd[k] > 0.0) P += z[k] * z[k] * Bd[k]; else Q += z[k] * z[k] * Bd[k];
@@ -313,7 +328,7 @@ static void arrow_inv_shift_value(int64_t N, const double *D, const double *z, d
     D1[N] = 0.0;
     u1[N] = -1.0;
     double as = a - sigma;
-    double P = 0.0, Q = 0.0;
+    acc_t P = 0.0, Q = 0.0;
     *Qout = 0;
     for (int64_t k = 0; k < N; ++k) {
         if (D1[k] > 0.0) P += z[k] * z[k] * D1[k]; else Q += z[k] * z[k] * D1[k];
@@ -408,7 +423,7 @@ static void symarrow_k(int64_t N, const double *D, const double *z, double a, in
                 nu = bisect_dpr1(s->d1, s->u1, rho, N + 1, 'L', s->w, &steps);
             double mD = fabs(s->d1[0]);
             for (int64_t l = 1; l <= N; ++l) mD = jl_max(mD, fabs(s->d1[l]));
-            double uu = 0.0;
+            acc_t uu = 0.0;
             for (int64_t l = 0; l <= N; ++l) uu += s->u1[l] * s->u1[l];
             nu1 = mD + fabs(rho) * uu;
             Knu = nu1 / fabs(nu);
@@ -420,7 +435,7 @@ static void symarrow_k(int64_t N, const double *D, const double *z, double a, in
         for (int64_t l = 0; l < N; ++l) v[l] = z[l] / ((D[l] - sigma) - mu);
         v[N] = -1.0;
         lambda = mu + sigma;
-        double ss = 0.0;
+        acc_t ss = 0.0;
         for (int64_t l = 0; l < n; ++l) ss += v[l] * v[l];
         double inrm = 1.0 / sqrt(ss);
         for (int64_t l = 0; l < n; ++l) v[l] *= inrm;
@@ -470,7 +485,7 @@ static void dpr1_inv_shift_index(int64_t n, const double *D, const double *u, do
         Bd[k - 1] = 1.0 / (D[k] - sigma);
         Bz[k - 1] = -u[k] * Bd[k - 1] * wz;
     }
-    double P = 0.0, Q = 0.0;
+    acc_t P = 0.0, Q = 0.0;
     *Qout = 0;
     for (int64_t k = 0; k < ii; ++k) {
         if (Bd[k] > 0.0) P += u[k] * u[k] * Bd[k]; else Q += u[k] * u[k] * Bd[k];
@@ -517,7 +532,7 @@ static void dpr1_inv_shift_value(int64_t n, const double *D, const double *u, do
         D1[k] = 1.0 / (D[k] - sigma);
         u1[k] = u[k] * D1[k];
     }
-    double P = 0.0, Q = 0.0;
+    acc_t P = 0.0, Q = 0.0;
     *Qout = 0;
     for (int64_t k = 0; k < n; ++k) {
         if (D1[k] > 0.0) P += u[k] * u[k] * D1[k]; else Q += u[k] * u[k] * D1[k];
@@ -601,7 +616,7 @@ static void symdpr1_k(int64_t n, const double *D, const double *u, double r, int
             nu = bisect_dpr1(s->d1, s->u1, rho, n, side, s->w, &steps);
             double mD = fabs(s->d1[0]);
             for (int64_t l = 1; l < n; ++l) mD = jl_max(mD, fabs(s->d1[l]));
-            double uu = 0.0;
+            acc_t uu = 0.0;
             for (int64_t l = 0; l < n; ++l) uu += s->u1[l] * s->u1[l];
             nu1 = mD + fabs(rho) * uu;
             Knu = nu1 / fabs(nu);
@@ -612,7 +627,7 @@ static void symdpr1_k(int64_t n, const double *D, const double *u, double r, int
         double mu = 1.0 / nu;
         for (int64_t l = 0; l < n; ++l) v[l] = u[l] / ((D[l] - sigma) - mu);
         lambda = mu + sigma;
-        double ss = 0.0;
+        acc_t ss = 0.0;
         for (int64_t l = 0; l < n; ++l) ss += v[l] * v[l];
         double inrm = 1.0 / sqrt(ss);
         for (int64_t l = 0; l < n; ++l) v[l] *= inrm;
@@ -671,7 +686,7 @@ static void half_inv_shift_index(int64_t nd, int64_t nz, const double *D, const 
     }
     dd ad = half_a_dd(nz, z, sigma);
     double a = ad.hi + ad.lo;
-    double P = 0.0, Q = 0.0;
+    acc_t P = 0.0, Q = 0.0;
     *Qout = 0;
     for (int64_t k = 0; k < ii; ++k) {
         if (Bd[k] > 0.0) P += z1[k] * z1[k] * Bd[k]; else Q += z1[k] * z1[k] * Bd[k];
@@ -719,7 +734,7 @@ static void half_inv_shift_value(int64_t nd, int64_t nz, const double *D, const 
     }
     D1[nd] = 0.0;
     u1[nd] = -1.0;
-    double P = 0.0, Q = 0.0;
+    acc_t P = 0.0, Q = 0.0;
     *Qout = 0;
     dd ad = half_a_dd(nz, z, sigma);
     double a = ad.hi + ad.lo;
@@ -771,7 +786,7 @@ static void halfarrow_k(int64_t nd, int64_t nz, const double *D, const double *z
     else if (k == n) { sigma = D[nd - 1]; i = nd; side = 'L'; }
     else {
         double Dk = D[k - 1];
-        double zz = 0.0;
+        acc_t zz = 0.0;
         for (int64_t l = 0; l < nz; ++l) zz += z[l] * z[l];
         double atemp = zz - Dk * Dk;
         double middle = ((D[k - 2] - Dk) * (D[k - 2] + Dk)) / 2.0;
@@ -829,7 +844,7 @@ static void halfarrow_k(int64_t nd, int64_t nz, const double *D, const double *z
         if (have_vec) {
             for (int64_t l = 0; l < nd; ++l) v[l] = z1[l] / ((D[l] - sig_v) * (D[l] + sig_v) - mu_v);
             v[nd] = -1.0;
-            double ss = 0.0;
+            acc_t ss = 0.0;
             for (int64_t l = 0; l < n; ++l) ss += v[l] * v[l];
             double inrm = 1.0 / sqrt(ss);
             for (int64_t l = 0; l < n; ++l) v[l] *= inrm;

@@ -12,23 +12,27 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "arrowhead_oracle.c")
 _OUT = os.path.join(_HERE, "_build", "liboracle.so")
+_OUT_HI = os.path.join(_HERE, "_build", "liboracle_hi.so")
 
 # -ffp-contract=off: Julia never contracts a*b+c into an FMA; the restatement must not either.
 _CFLAGS = ["-O2", "-std=c11", "-fPIC", "-fopenmp", "-ffp-contract=off", "-fno-fast-math"]
 
 
-def build(force: bool = False) -> str:
-    """Compile the C restatement with the PATH gcc (the image's $CC has no libgomp.spec)."""
-    if not force and os.path.exists(_OUT) and os.path.getmtime(_OUT) >= os.path.getmtime(_SRC):
-        return _OUT
+def build(force: bool = False, hi: bool = False) -> str:
+    """Compile the C restatement with the PATH gcc (the image's $CC has no libgomp.spec).
+    hi=True builds the -DAH_ORACLE_HI variant (long-double accumulators, same algorithm)."""
+    out = _OUT_HI if hi else _OUT
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(_SRC):
+        return out
     gcc = shutil.which("gcc")
     if gcc is None:
         raise RuntimeError("oracle: gcc not found on PATH")
-    os.makedirs(os.path.dirname(_OUT), exist_ok=True)
-    tmp = _OUT + f".tmp{os.getpid()}"
-    subprocess.run([gcc, *_CFLAGS, "-shared", "-o", tmp, _SRC, "-lm"], check=True)
-    os.replace(tmp, _OUT)
-    return _OUT
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    tmp = out + f".tmp{os.getpid()}"
+    extra = ["-DAH_ORACLE_HI"] if hi else []
+    subprocess.run([gcc, *_CFLAGS, *extra, "-shared", "-o", tmp, _SRC, "-lm"], check=True)
+    os.replace(tmp, out)
+    return out
 
 
 _dp = C.POINTER(C.c_double)
@@ -149,6 +153,7 @@ class OracleLib:
 
 
 _LIB: OracleLib | None = None
+_LIB_HI: OracleLib | None = None
 
 
 def get_lib() -> OracleLib:
@@ -156,3 +161,11 @@ def get_lib() -> OracleLib:
     if _LIB is None:
         _LIB = OracleLib()
     return _LIB
+
+
+def get_lib_hi() -> OracleLib:
+    """Same algorithm with long-double accumulators: the accuracy yardstick, not the reference's rounding."""
+    global _LIB_HI
+    if _LIB_HI is None:
+        _LIB_HI = OracleLib(build(hi=True))
+    return _LIB_HI

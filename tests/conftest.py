@@ -44,6 +44,13 @@ def oracle_lib():
 
 
 @pytest.fixture(scope="session")
+def oracle_hi():
+    """same algorithm, long-double accumulators (measures the reference's own summation noise)"""
+    import oracle
+    return oracle.get_lib_hi()
+
+
+@pytest.fixture(scope="session")
 def gpu_ctx():
     import arrowhead_b200 as ab
     ab.build_library()
