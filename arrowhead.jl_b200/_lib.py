@@ -36,6 +36,7 @@ class AhStats(C.Structure):
         ("kernel_ms", C.c_double), ("main_kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("launches", C.c_int64), ("n_fast", C.c_int64), ("n_full", C.c_int64), ("total_steps", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("prep_ms", C.c_double), ("bisect_ms", C.c_double), ("vec_ms", C.c_double), ("full_ms", C.c_double),
     ]
 
     def asdict(self):

@@ -18,7 +18,7 @@
 
 #include "ah_device.cuh"
 #include "ah_full.cuh"
-#include "ah_fast.cuh"
+#include "ah_pipe.cuh"
 
 namespace {
 
@@ -37,15 +37,15 @@ struct ah_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t stream = nullptr;  // the stream kernels run on (own_stream or caller's)
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[12] = {};
     cudaEvent_t ev_stage[2] = {};
     std::string err;
     int mode = 0;
     ah_stats stats = {};
-    DevBuf dD, dW, dZ, dMap1, dMap2, dScale, dOut, dList, dCount, dStage[2];
+    DevBuf dD, dW, dW2, dKs, dZ, dMap1, dMap2, dScale, dOut, dList, dCount, dStage[2];
     void *hPinned = nullptr;  // pinned bounce buffer for the per-k outputs
     size_t hPinnedCap = 0;
-    std::vector<double> hPadD, hPadW;
+    std::vector<double> hPadD, hPadW, hPadW2;
     unsigned long long *hCounts = nullptr;  // pinned, 64 entries: per-block hand-over counts of the last call
 };
 
@@ -167,31 +167,36 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     // ---- inputs -> device, padded to whole tiles of the fast kernel's ring.  Pad poles lie strictly
     // below every real pole (so no shift or bisection point can hit them) and carry weight 0.
     int rc;
-    const int64_t Np = ((N + ah::FTL - 1) / ah::FTL) * ah::FTL;
+    const int64_t Np = ((N + ah::TILE_POLES - 1) / ah::TILE_POLES) * ah::TILE_POLES;
     ctx->hPadD.assign((size_t)Np, 0.0);
     ctx->hPadW.assign((size_t)Np, 0.0);
+    ctx->hPadW2.assign((size_t)Np, 0.0);
     std::memcpy(ctx->hPadD.data(), hD, N * 8);
     std::memcpy(ctx->hPadW.data(), hW, N * 8);
-    {
-        double pad;
-        if (L.kind == KIND_HALF) {
-            pad = hD[N - 1] / 2.0;
-        } else {
-            double span = hD[0] - hD[N - 1];
-            if (!(span > 0.0)) span = std::max(std::fabs(hD[N - 1]), 1.0);
-            pad = hD[N - 1] - span;
-            if (!std::isfinite(pad)) pad = -1.7976931348623157e308;
-        }
-        for (int64_t l = N; l < Np; ++l) ctx->hPadD[l] = pad;
+    for (int64_t l = 0; l < N; ++l) ctx->hPadW2[l] = hW[l] * hW[l];   // one rounding, as z[k]^2 in the reference
+    double pad;
+    if (L.kind == KIND_HALF) {
+        pad = hD[N - 1] / 2.0;
+    } else {
+        double span = hD[0] - hD[N - 1];
+        if (!(span > 0.0)) span = std::max(std::fabs(hD[N - 1]), 1.0);
+        pad = hD[N - 1] - span;
+        if (!std::isfinite(pad)) pad = -1.7976931348623157e308;
     }
+    for (int64_t l = N; l < Np; ++l) ctx->hPadD[l] = pad;
     if ((rc = ensure(ctx, ctx->dD, Np * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dW, Np * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dW2, Np * 8))) return rc;
     AH_CUDA(cudaEventRecord(ctx->ev[0], st));
     AH_CUDA(cudaMemcpyAsync(ctx->dD.p, ctx->hPadD.data(), Np * 8, cudaMemcpyHostToDevice, st));
     AH_CUDA(cudaMemcpyAsync(ctx->dW.p, ctx->hPadW.data(), Np * 8, cudaMemcpyHostToDevice, st));
-    ctx->stats.h2d_bytes += 2 * Np * 8;
+    AH_CUDA(cudaMemcpyAsync(ctx->dW2.p, ctx->hPadW2.data(), Np * 8, cudaMemcpyHostToDevice, st));
+    ctx->stats.h2d_bytes += 3 * Np * 8;
     P.D = (const double *)ctx->dD.p;
     P.w = (const double *)ctx->dW.p;
+    P.w2 = (const double *)ctx->dW2.p;
+    P.Np = Np;
+    P.pad = pad;
     P.z = nullptr;
     if (hZ) {
         if ((rc = ensure(ctx, ctx->dZ, N * 8))) return rc;
@@ -235,6 +240,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         O.status = carve<int32_t>(p, cnt);
     }
     if ((rc = ensure(ctx, ctx->dList, cnt * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dKs, (size_t)cnt * sizeof(ah::KState)))) return rc;
     if ((rc = ensure(ctx, ctx->dCount, 256))) return rc;
 
     // ---- eigenvector destination: device-resident, or host through a double-buffered staging area
@@ -280,10 +286,20 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         unsigned long long *dcount = (unsigned long long *)ctx->dCount.p;
         AH_CUDA(cudaEventRecord(ctx->ev[2], st));
         if (ctx->mode == 0) {
+            KState *ks = (KState *)ctx->dKs.p;
             AH_CUDA(cudaMemsetAsync(dcount, 0, 16, st));
-            rc = ah::launch_fast(L.kind, P, Oc, kb, cc, dlist, dcount, ctx->sm_count, st);
-            if (rc) return cuda_fail(ctx, (cudaError_t)rc, "fast kernel launch");
-            ctx->stats.launches += 1;
+            rc = ah::launch_prep(L.kind, P, ks, kb, cc, dlist, dcount, st);
+            if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_prep launch");
+            AH_CUDA(cudaEventRecord(ctx->ev[8], st));
+            rc = ah::launch_bisect(L.kind, P, Oc, ks, kb, cc, dlist, dcount, ctx->sm_count, st);
+            if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect launch");
+            AH_CUDA(cudaEventRecord(ctx->ev[9], st));
+            ctx->stats.launches += 2;
+            if (wantU || wantV) {
+                rc = ah::launch_vec(L.kind, P, Oc, ks, kb, cc, st);
+                if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_vec launch");
+                ctx->stats.launches += 1;
+            }
             AH_CUDA(cudaEventRecord(ctx->ev[3], st));
             {
                 // the hand-over list is consumed straight from device memory; a few hundred CTAs cover the
@@ -333,11 +349,20 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         }
         // accumulate kernel times of this block (needs the events complete)
         AH_CUDA(cudaEventSynchronize(ctx->ev[4]));
-        float t1 = 0.f, t2 = 0.f;
-        AH_CUDA(cudaEventElapsedTime(&t1, ctx->ev[2], ctx->ev[3]));
+        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
         AH_CUDA(cudaEventElapsedTime(&t2, ctx->ev[2], ctx->ev[4]));
-        ms_main += t1;
         ms_all += t2;
+        AH_CUDA(cudaEventElapsedTime(&t3, ctx->ev[3], ctx->ev[4]));
+        ctx->stats.full_ms += t3;
+        if (ctx->mode == 0) {
+            AH_CUDA(cudaEventElapsedTime(&t1, ctx->ev[2], ctx->ev[8]));
+            ctx->stats.prep_ms += t1;
+            AH_CUDA(cudaEventElapsedTime(&t1, ctx->ev[8], ctx->ev[9]));
+            ctx->stats.bisect_ms += t1;
+            ms_main += t1;
+            AH_CUDA(cudaEventElapsedTime(&t1, ctx->ev[9], ctx->ev[3]));
+            ctx->stats.vec_ms += t1;
+        }
     }
 
     // ---- per-k outputs -> host
@@ -459,7 +484,7 @@ int ah_create(ah_ctx **pctx, int device) {
     for (auto &ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     for (auto &ev : ctx->ev_stage) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaMallocHost((void **)&ctx->hCounts, 64 * sizeof(unsigned long long)) == cudaSuccess;
-    if (ok) ok = ah::configure_fast_kernels() == 0;
+    if (ok) ok = ah::configure_pipe_kernels() == 0;
     if (!ok) {
         cudaError_t le = cudaGetLastError();
         ah_destroy(ctx);
@@ -473,7 +498,7 @@ int ah_create(ah_ctx **pctx, int device) {
 void ah_destroy(ah_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf *b : {&ctx->dD, &ctx->dW, &ctx->dZ, &ctx->dMap1, &ctx->dMap2, &ctx->dScale, &ctx->dOut, &ctx->dList,
+    for (DevBuf *b : {&ctx->dD, &ctx->dW, &ctx->dW2, &ctx->dKs, &ctx->dZ, &ctx->dMap1, &ctx->dMap2, &ctx->dScale, &ctx->dOut, &ctx->dList,
                       &ctx->dCount, &ctx->dStage[0], &ctx->dStage[1]})
         if (b->p) cudaFree(b->p);
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);

@@ -26,6 +26,9 @@ struct Problem {
     int64_t N;         // number of poles
     const double *D;   // [N] strictly decreasing
     const double *w;   // [N] z (arrow) | u (dpr1) | z.*D (half)
+    const double *w2;  // [Np] w_l^2 (fast path)
+    int64_t Np;        // D, w, w2 are padded to Np poles (multiple of the fast path's tile); pads: weight 0, D = pad
+    double pad;        // pad pole: strictly below every real pole
     const double *z;   // [N] half only: the original z (double-double branch needs it)
     double a;          // arrow: arrow top; dpr1: rho (>0)
     double maxabs_w;   // max_l |w_l|

@@ -1,0 +1,693 @@
+// ah_pipe.cuh -- the fast path: standard (no-remedy, binary64) eigenpairs as a three-kernel pipeline.
+//
+// Every O(N) loop of the reference's per-k solver is a "sweep" over the poles l = 0..N-1:
+//
+//   k_prep    SHIFT   sum_l w_l^2 / ((D_l - D_k) - mid)                 arrowhead3.jl:437-441
+//             INV     P,Q, sum|z'|, max(D'+|z'|), max(|D'|+|z'|)        arrowhead3.jl:152-189, brackets :671-680, nu_1 :460-464
+//   k_bisect  BISECT  sum_l z'_l^2/(D'_l - m), ~54 sweeps per eigenpair  arrowhead3.jl:686-704      <- ~90 % of all work
+//   k_vec     VNORM   sum_l v_l^2,  v_l = w_l/((D_l - sigma) - mu)      arrowhead3.jl:517-522
+//             VWRITE  v_l / ||v||  -> U[:,k]  (recomputed, not re-read)  arrowhead3.jl:522, 643
+//
+// (arrowhead4.jl / arrowhead6.jl are the same loops with the DPR1 / HalfArrow term formulas, selected
+// by the KIND template parameter.)  The per-eigenpair scalars travel between the kernels in a 128-byte
+// KState record; nothing of size N is ever materialised per eigenpair -- the inverse (D', z') of the
+// reference exists only as the formula  z'_l^2/(D'_l - m) = wz^2 * w_l^2 / (d_l (1 - m d_l)),  d_l = D_l - sigma.
+//
+// k_bisect is the hot kernel: persistent, one CTA of 16 warps per SM.  D and w^2 stream over and over
+// through a shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier); one tile =
+// 2048 poles.  A CTA bisects BJ = 8 eigenpairs ("slots") at once: each thread moves its 4 poles of the
+// tile from shared memory into registers once and evaluates the term for all 8 slots from there, so
+// L2 and shared-memory traffic per term drop 8x and the FP64 pipe is the only busy unit.  One term is
+// 7 FP64-pipe instructions (DADD d, DFMA e=1-m d, DMUL t=d e, MUFU.RCP64H seed + 3 DFMA, DFMA accumulate).
+// The inner block is branch-free: the one pole per slot that must be skipped (the shift pole, d = 0) is
+// handled by its owner thread, which adds that pole's terms for the other slots on a rare side path and
+// then replaces its register copy by a harmless (pad pole, weight 0) pair.
+// A sweep ends with a fixed-order reduction (thread-sequential, xor-shuffle tree, warps 0..15); warp j
+// then advances slot j's bisection state, finalises a converged eigenpair (Knu test, Remedy-1 test) and
+// pulls the next k from a global counter, so all 8 slots stay busy until the work runs out.
+// Anything non-standard (double-double needed, Knu > tolnu -> Remedy 3, Remedy 1, |nu| = Inf) is
+// appended to a hand-over list and solved by k_full (ah_full.cuh).
+#pragma once
+#include "ah_device.cuh"
+#include "ah_full.cuh"
+
+namespace ah {
+
+enum : int { KS_READY = 0, KS_HANDOFF = 1, KS_DONE = 2 };
+
+struct KState {   // 128 bytes per eigenpair
+    double sigma, wz, b, left, right, nu1, Kb, Kz;   // written by k_prep
+    double nu, mu, lambda, knu;                       // written by k_bisect
+    int64_t i;                                        // shift index, 1-based
+    int32_t sideR, flag, steps, pad_;
+    double spare_;
+};
+static_assert(sizeof(KState) == 128, "KState layout");
+
+// ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(void *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+
+// D'_l = 1/d_l for a single pole (bracket ends are the neighbours of the shift, no reduction needed)
+template <int KIND>
+__device__ __forceinline__ double inv_pole(const double *D, int64_t l, double sigma) {
+    return __ddiv_rn(1.0, dshift<KIND>(D[l], sigma));
+}
+
+// =====================================================================================================
+// k_prep: shift selection + shifted inverse, PJ consecutive eigenpairs per CTA
+constexpr int PT = 256, PW = PT / 32, PJ = 4;
+
+template <int KIND>
+__global__ void __launch_bounds__(PT, 2)
+k_prep(Problem P, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *__restrict__ dlist,
+       unsigned long long *dcount) {
+    __shared__ double red[PJ * 5][PW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t N = P.N, Np = P.Np;
+    const double *__restrict__ D = P.D;
+    const double *__restrict__ W = P.w;
+    const int64_t c0 = (int64_t)blockIdx.x * PJ;
+
+    int64_t kk[PJ];
+    bool valid[PJ], ext[PJ];
+    double Dk[PJ], mid[PJ];
+#pragma unroll
+    for (int j = 0; j < PJ; ++j) {
+        valid[j] = c0 + j < cnt;
+        kk[j] = kbase + (valid[j] ? c0 + j : c0);
+        const int64_t k = kk[j];
+        ext[j] = (k == 1) || (KIND != KIND_DPR1 && k == N + 1);
+        if (!ext[j]) {
+            Dk[j] = D[k - 1];
+            mid[j] = dshift<KIND>(D[k - 2], Dk[j]) / 2.0;
+        } else {   // no shift test for the two exterior eigenvalues; harmless dummy sweep
+            Dk[j] = D[0];
+            mid[j] = 1.0;
+        }
+    }
+
+    // ---- SHIFT sweep (pads carry weight 0 and lie below every pole: their terms are exact zeros)
+    double xs[PJ];
+#pragma unroll
+    for (int j = 0; j < PJ; ++j) xs[j] = 0.0;
+    for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * PT) {
+        const double2 d2 = ldg2(D + l0), w2 = ldg2(W + l0);
+        const double dv[2] = {d2.x, d2.y};
+        const double w2v[2] = {__dmul_rn(w2.x, w2.x), __dmul_rn(w2.y, w2.y)};
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < PJ; ++j)
+                xs[j] = __dadd_rn(xs[j], __ddiv_rn(w2v[h], __dadd_rn(dshift<KIND>(dv[h], Dk[j]), -mid[j])));
+    }
+#pragma unroll
+    for (int j = 0; j < PJ; ++j) {
+        const double v = warp_allreduce(xs[j], OpSum());
+        if (lane == 0) red[j][warp] = v;
+    }
+    __syncthreads();
+    int64_t ii[PJ];
+    bool sideR[PJ];
+    double sigma[PJ], wz[PJ], sgn[PJ];
+#pragma unroll
+    for (int j = 0; j < PJ; ++j) {
+        double S = red[j][0];
+        for (int w = 1; w < PW; ++w) S = __dadd_rn(S, red[j][w]);
+        const int64_t k = kk[j];
+        int64_t i;
+        if (ext[j]) {
+            i = (k == 1) ? 1 : N;
+            sideR[j] = (k == 1);
+        } else {
+            bool right;
+            if (KIND == KIND_ARROW) right = __dadd_rn(__dadd_rn(__dadd_rn(P.a, -Dk[j]), -mid[j]), -S) < 0.0;
+            else if (KIND == KIND_HALF) right = __dadd_rn(__dadd_rn(__dadd_rn(P.zz, -__dmul_rn(Dk[j], Dk[j])), -mid[j]), -S) < 0.0;
+            else right = __dadd_rn(1.0, __dmul_rn(P.a, S)) > 0.0;
+            i = right ? k : k - 1;
+            sideR[j] = right;
+        }
+        ii[j] = i - 1;
+        sigma[j] = D[ii[j]];
+        wz[j] = __ddiv_rn(1.0, W[ii[j]]);
+        sgn[j] = sideR[j] ? 1.0 : -1.0;
+    }
+    __syncthreads();
+
+    // ---- INV sweep: exact reference arithmetic for every entry of the inverse
+    double a0[PJ], a1[PJ], a2[PJ], a3[PJ], a4[PJ];
+#pragma unroll
+    for (int j = 0; j < PJ; ++j) { a0[j] = 0.0; a1[j] = 0.0; a2[j] = 0.0; a3[j] = -INFINITY; a4[j] = 0.0; }
+    for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * PT) {
+        const double2 d2 = ldg2(D + l0), w2 = ldg2(W + l0);
+        const double dv[2] = {d2.x, d2.y};
+        const double wv[2] = {w2.x, w2.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t l = l0 + h;
+            const double W2 = __dmul_rn(wv[h], wv[h]);
+            if (l < N) {
+#pragma unroll
+                for (int j = 0; j < PJ; ++j) {
+                    if (l != ii[j]) {
+                        const double Dp = __ddiv_rn(1.0, dshift<KIND>(dv[h], sigma[j]));
+                        const double zp = __dmul_rn(__dmul_rn(-wv[h], Dp), wz[j]);
+                        const double t = __dmul_rn(W2, Dp);
+                        if (Dp > 0.0) a0[j] = __dadd_rn(a0[j], t); else a1[j] = __dadd_rn(a1[j], t);
+                        const double az = fabs(zp);
+                        a2[j] = __dadd_rn(a2[j], az);
+                        a3[j] = fmax(a3[j], __dadd_rn(__dmul_rn(sgn[j], Dp), az));
+                        a4[j] = fmax(a4[j], __dadd_rn(fabs(Dp), az));
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < PJ; ++j) {
+        const double v0 = warp_allreduce(a0[j], OpSum()), v1 = warp_allreduce(a1[j], OpSum());
+        const double v2 = warp_allreduce(a2[j], OpSum()), v3 = warp_allreduce(a3[j], OpMax());
+        const double v4 = warp_allreduce(a4[j], OpMax());
+        if (lane == 0) {
+            red[j * 5 + 0][warp] = v0; red[j * 5 + 1][warp] = v1; red[j * 5 + 2][warp] = v2;
+            red[j * 5 + 3][warp] = v3; red[j * 5 + 4][warp] = v4;
+        }
+    }
+    __syncthreads();
+    if (tid < PJ && valid[0]) {
+        // one thread per slot finishes the scalars (the per-slot arrays above are fully unrolled
+        // registers, so pick this thread's slot with a static loop)
+#pragma unroll
+        for (int j = 0; j < PJ; ++j) {
+            if (j != tid || !valid[j]) continue;
+            double Ps = red[j * 5][0], Qs = red[j * 5 + 1][0], sabs = red[j * 5 + 2][0], bnd = red[j * 5 + 3][0],
+                   nu1m = red[j * 5 + 4][0];
+            for (int w = 1; w < PW; ++w) {
+                Ps = __dadd_rn(Ps, red[j * 5][w]); Qs = __dadd_rn(Qs, red[j * 5 + 1][w]);
+                sabs = __dadd_rn(sabs, red[j * 5 + 2][w]);
+                bnd = fmax(bnd, red[j * 5 + 3][w]); nu1m = fmax(nu1m, red[j * 5 + 4][w]);
+            }
+            const int64_t i0 = ii[j];
+            const double sg = sigma[j], wzj = wz[j];
+            // neighbours of the shift give max D' / min D' (D strictly decreasing)
+            double mxD, mnD;
+            if (KIND == KIND_DPR1) {
+                mxD = i0 > 0 ? inv_pole<KIND>(D, i0 - 1, sg) : inv_pole<KIND>(D, N - 1, sg);
+                mnD = i0 < N - 1 ? inv_pole<KIND>(D, i0 + 1, sg) : inv_pole<KIND>(D, 0, sg);
+            } else {
+                mxD = i0 > 0 ? inv_pole<KIND>(D, i0 - 1, sg) : 0.0;
+                mnD = i0 < N - 1 ? inv_pole<KIND>(D, i0 + 1, sg) : 0.0;
+                const double az = fabs(wzj);   // the slot (0, wz) of the inverse arrow
+                sabs = __dadd_rn(sabs, az);
+                bnd = fmax(bnd, az);
+                nu1m = fmax(nu1m, az);
+            }
+            if (KIND == KIND_ARROW) {
+                const double as_ = __dadd_rn(P.a, -sg);
+                if (as_ < 0) Ps = __dadd_rn(Ps, -as_); else Qs = __dadd_rn(Qs, -as_);
+            } else if (KIND == KIND_HALF) {
+                const dd ad = dd_add(dd{P.zz_hi, P.zz_lo}, dd_mul(dd_from(sg), dd_from(-sg)));
+                const double as_ = __dadd_rn(ad.hi, ad.lo);
+                if (as_ < 0) Ps = __dadd_rn(Ps, -as_); else Qs = __dadd_rn(Qs, -as_);
+            } else {
+                const double ir = __ddiv_rn(1.0, P.a);
+                if (P.a > 0) Ps = __dadd_rn(Ps, ir); else Qs = __dadd_rn(Qs, ir);
+            }
+            const double PQ = __dadd_rn(Ps, Qs);
+            KState S;
+            S.sigma = sg; S.wz = wzj; S.i = i0 + 1; S.sideR = sideR[j] ? 1 : 0;
+            S.Kb = __ddiv_rn(__dadd_rn(Ps, -Qs), fabs(PQ));
+            if (KIND == KIND_DPR1) S.Kz = __dmul_rn(__dadd_rn(P.sumabs_w, -fabs(W[i0])), fabs(wzj));
+            else S.Kz = __dmul_rn(P.maxabs_w, fabs(wzj));
+            S.nu = 0.0; S.mu = 0.0; S.lambda = 0.0; S.knu = 0.0; S.steps = 0; S.pad_ = 0; S.spare_ = 0.0;
+            if (S.Kb < P.tau[0] || S.Kz < P.tau[1]) {
+                S.b = __dmul_rn(__dmul_rn(PQ, wzj), wzj);
+                S.nu1 = fmax(__dadd_rn(sabs, fabs(S.b)), nu1m);
+                if (sideR[j]) { S.left = mxD; S.right = fmax(bnd, __dadd_rn(S.b, sabs)); }
+                else { S.left = fmin(-bnd, __dadd_rn(S.b, -sabs)); S.right = mnD; }
+                S.flag = KS_READY;
+            } else {   // double-double (or BigFloat) needed: full kernel
+                S.b = 0.0; S.nu1 = 0.0; S.left = 0.0; S.right = 0.0;
+                S.flag = KS_HANDOFF;
+                dlist[atomicAdd(dcount, 1ull)] = kk[j];
+            }
+            ks[c0 + j] = S;
+        }
+    }
+}
+
+// =====================================================================================================
+// k_bisect
+constexpr int BT = 512;          // threads per CTA
+constexpr int BW = BT / 32;      // warps
+constexpr int BJ = 8;            // eigenpair slots per CTA
+constexpr int BE = 4;            // poles per thread per tile
+constexpr int BTL = BT * BE;     // poles per tile (2048)
+constexpr int BS = 4;            // ring stages
+constexpr int TILE_POLES = BTL;  // inputs are padded to a multiple of this
+
+enum : int { PH_FREE = 0, PH_BISECT, PH_DONE };
+
+struct BSlot {   // cold per-slot state, touched by warp j only
+    int64_t k, i;
+    int phase, sideR, steps, pad_;
+    double sigma, wz2, b, left, right, m, nu1, Kb, Kz;
+};
+struct BisectShared {
+    alignas(128) double tileD[BS][BTL];
+    alignas(128) double tileW[BS][BTL];
+    alignas(8) unsigned long long full[BS];
+    alignas(8) unsigned long long empty[BS];
+    alignas(16) double2 hot[BJ];   // (sigma, m) of every slot for the coming sweep
+    double part[BJ][BW];
+    long long skip[BJ];            // 0-based index of the slot's shift pole, -1: slot idle
+    BSlot slot[BJ];
+};
+
+// element e (0..BE-1) of thread t in a tile sits at offset (e>>1)*2*BT + 2*t + (e&1):
+// consecutive lanes read consecutive 16-byte pairs -> conflict-free LDS.128.
+__device__ __forceinline__ int elem_offset(int t, int e) { return (e >> 1) * (2 * BT) + 2 * t + (e & 1); }
+
+template <int KIND>
+__device__ __forceinline__ void bisect_finalize(const Problem &P, const Outputs &O, KState *ks, BSlot &S, int64_t kbase,
+                                                int64_t *dlist, unsigned long long *dcount, int lane) {
+    const int64_t N = P.N;
+    const double nu = S.right;
+    const int64_t ii = S.i - 1;
+    const double Knu = __ddiv_rn(S.nu1, fabs(nu));
+    bool bail = !isfinite(nu);
+    if (KIND == KIND_HALF) bail = bail || !(Knu < P.tau[2]);
+    else bail = bail || (Knu > P.tau[2]);
+    double mu = 0.0, lambda = 0.0;
+    if (!bail) {
+        mu = __ddiv_rn(1.0, nu);
+        const double Di = P.D[ii];
+        if (KIND == KIND_HALF) {
+            lambda = sqrt(__dadd_rn(mu, __dmul_rn(S.sigma, S.sigma)));
+            bail = (S.k == N + 1) &&
+                   (__ddiv_rn(__dadd_rn(__dmul_rn(Di, Di), fabs(mu)), fabs(__dmul_rn(lambda, lambda))) > P.tau[4]);
+        } else {
+            lambda = __dadd_rn(mu, S.sigma);
+            if (__ddiv_rn(__dadd_rn(fabs(Di), fabs(mu)), fabs(lambda)) > P.tau[4]) {   // Remedy 1 wanted?
+                const int64_t k = S.k, i = S.i;
+                const bool c1 = (k == 1 && P.D[0] < 0.0);
+                const bool c2 = (KIND == KIND_ARROW) && (k == N + 1 && P.D[N - 1] > 0.0);
+                const bool c3 = (KIND == KIND_ARROW ? i < N : true) && !S.sideR &&
+                                sign_jl(Di) + sign_jl(P.D[ii + 1 < N ? ii + 1 : ii]) == 0.0;
+                const bool c4 = (i > 1 && S.sideR && sign_jl(Di) + sign_jl(P.D[ii > 0 ? ii - 1 : 0]) == 0.0);
+                bail = c1 || c2 || c3 || c4;
+            }
+        }
+    }
+    if (lane == 0) {
+        const int64_t col = S.k - kbase;
+        KState &G = ks[col];
+        if (bail) {
+            G.flag = KS_HANDOFF;
+            dlist[atomicAdd(dcount, 1ull)] = S.k;
+        } else {
+            G.nu = nu; G.mu = mu; G.lambda = lambda; G.knu = Knu; G.steps = S.steps;
+            G.flag = KS_DONE;
+            O.lambda[col] = lambda;
+            O.sind[col] = S.i;
+            O.kb[col] = S.Kb; O.kz[col] = S.Kz; O.knu[col] = Knu; O.krho[col] = 0.0;
+            O.qout[col] = 0;
+            O.steps[col] = S.steps;
+            O.status[col] = 0;
+        }
+    }
+}
+
+__device__ __forceinline__ bool bisect_converged(const BSlot &S) {
+    return !((S.right - S.left) > 2.0 * kEps * fmax(fabs(S.left), fabs(S.right)));
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(BT, 1)
+k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *__restrict__ dlist,
+         unsigned long long *dcount) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BisectShared &sh = *reinterpret_cast<BisectShared *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntiles = (int)(P.Np / BTL);
+
+    if (tid == 0) {
+        for (int s = 0; s < BS; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], BW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < BJ) { sh.slot[tid].phase = PH_FREE; sh.skip[tid] = -1; sh.hot[tid] = make_double2(0.0, 0.0); }
+    __syncthreads();
+
+    long long g_issue = 0;   // tiles issued (thread 0 only)
+    long long g = 0;         // tiles consumed
+    auto issue_tile = [&](long long gi) {
+        const int s = (int)(gi % BS);
+        const long long use = gi / BS;
+        if (use > 0) mbar_wait(&sh.empty[s], (uint32_t)((use - 1) & 1));
+        const int tile = (int)(gi % ntiles);
+        mbar_arrive_expect_tx(&sh.full[s], 2u * BTL * 8u);
+        bulk_g2s(&sh.tileD[s][0], P.D + (int64_t)tile * BTL, BTL * 8u, &sh.full[s]);
+        bulk_g2s(&sh.tileW[s][0], P.w2 + (int64_t)tile * BTL, BTL * 8u, &sh.full[s]);
+    };
+    if (tid == 0) { for (; g_issue < BS - 1; ++g_issue) issue_tile(g_issue); }
+
+    bool first = true;
+    while (true) {
+        // ================= sweep boundary: warp j advances slot j =================
+        if (warp < BJ) {
+            BSlot &S = sh.slot[warp];
+            if (!first && S.phase == PH_BISECT) {
+                double sum = (lane < BW) ? sh.part[warp][lane] : 0.0;
+#pragma unroll
+                for (int o = BW / 2; o > 0; o >>= 1) {
+                    const double p = __shfl_xor_sync(0xffffffffu, sum, o);
+                    sum = (lane & o) ? __dadd_rn(p, sum) : __dadd_rn(sum, p);
+                }
+                sum = __shfl_sync(0xffffffffu, sum, 0);
+                sum = __dmul_rn(sum, S.wz2);
+                const double m = S.m;
+                if (KIND != KIND_DPR1) sum = __dadd_rn(sum, __ddiv_rn(S.wz2, __dadd_rn(0.0, -m)));
+                const double F = __dadd_rn(__dadd_rn(S.b, -m), -sum);
+                __syncwarp();
+                if (lane == 0) {
+                    if (F > 0.0) S.left = m; else S.right = m;
+                    S.m = (S.left + S.right) / 2.0;
+                    S.steps += 1;
+                }
+                __syncwarp();
+            }
+            // converged (the reference tests before the first step, too) -> finalise, then fetch new work
+            while (true) {
+                if (S.phase == PH_BISECT) {
+                    if (!bisect_converged(S)) break;
+                    bisect_finalize<KIND>(P, O, ks, S, kbase, dlist, dcount, lane);
+                    __syncwarp();
+                    if (lane == 0) S.phase = PH_FREE;
+                    __syncwarp();
+                }
+                if (S.phase == PH_DONE) break;
+                // PH_FREE: next eigenpair that k_prep left ready
+                unsigned long long wi = 0;
+                if (lane == 0) wi = atomicAdd(dcount + 1, 1ull);
+                wi = __shfl_sync(0xffffffffu, wi, 0);
+                if ((int64_t)wi >= cnt) {
+                    __syncwarp();
+                    if (lane == 0) S.phase = PH_DONE;
+                    __syncwarp();
+                    break;
+                }
+                const KState &G = ks[wi];
+                if (G.flag != KS_READY) continue;
+                __syncwarp();
+                if (lane == 0) {
+                    S.k = kbase + (int64_t)wi; S.i = G.i; S.sideR = G.sideR; S.steps = 0;
+                    S.sigma = G.sigma; S.wz2 = __dmul_rn(G.wz, G.wz); S.b = G.b;
+                    S.left = G.left; S.right = G.right; S.m = (G.left + G.right) / 2.0;
+                    S.nu1 = G.nu1; S.Kb = G.Kb; S.Kz = G.Kz;
+                    S.phase = PH_BISECT;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                const bool act = S.phase == PH_BISECT;
+                sh.hot[warp] = act ? make_double2(S.sigma, S.m) : make_double2(0.0, 0.0);
+                sh.skip[warp] = act ? (long long)(S.i - 1) : -1;
+            }
+        }
+        first = false;
+        __syncthreads();
+
+        // ================= per-thread copies of the sweep parameters =================
+        double sig[BJ], mm[BJ];
+        bool any_active = false;
+        unsigned fixmask = 0;
+        int fmin = 0x7fffffff, fmax_ = -1;
+#pragma unroll
+        for (int j = 0; j < BJ; ++j) {
+            const double2 h = sh.hot[j];
+            sig[j] = h.x; mm[j] = h.y;
+            const long long sk = sh.skip[j];
+            any_active = any_active || (sk >= 0);
+            if (sk >= 0) {
+                const int t_i = (int)(sk / BTL);
+                const int owner = (int)(((sk % BTL) % (2 * BT)) >> 1);
+                if (owner == tid) { fixmask |= 1u << j; fmin = min(fmin, t_i); fmax_ = max(fmax_, t_i); }
+            }
+        }
+        if (!any_active) break;
+        double acc[BJ];
+#pragma unroll
+        for (int j = 0; j < BJ; ++j) acc[j] = 0.0;
+
+        // ================= the sweep =================
+        for (int tile = 0; tile < ntiles; ++tile, ++g) {
+            if (tid == 0) { issue_tile(g_issue); ++g_issue; }
+            const int s = (int)(g % BS);
+            mbar_wait(&sh.full[s], (uint32_t)((g / BS) & 1));
+            double Dv[BE], W2[BE];
+#pragma unroll
+            for (int e = 0; e < BE; e += 2) {
+                const double2 d2 = *reinterpret_cast<const double2 *>(&sh.tileD[s][elem_offset(tid, e)]);
+                const double2 w2 = *reinterpret_cast<const double2 *>(&sh.tileW[s][elem_offset(tid, e)]);
+                Dv[e] = d2.x; Dv[e + 1] = d2.y; W2[e] = w2.x; W2[e + 1] = w2.y;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.empty[s]);
+
+            if (fixmask != 0 && tile >= fmin && tile <= fmax_) {
+                // rare: this thread holds the shift pole of some slot(s) in this tile.  Add the pole's
+                // terms for all OTHER slots here, then neutralise the register copy for the main block.
+                const long long base = (long long)tile * BTL;
+#pragma unroll
+                for (int e = 0; e < BE; ++e) {
+                    const long long l = base + elem_offset(tid, e);
+                    bool hit = false;
+#pragma unroll
+                    for (int j = 0; j < BJ; ++j) hit = hit || (sh.skip[j] == l);
+                    if (hit) {
+#pragma unroll
+                        for (int j = 0; j < BJ; ++j)
+                            if (sh.skip[j] != l)
+                                acc[j] = secular_term_acc(acc[j], dshift<KIND>(Dv[e], sig[j]), mm[j], W2[e]);
+                        Dv[e] = P.pad;
+                        W2[e] = 0.0;
+                    }
+                }
+            }
+
+            // ---- the branch-free block: BE x BJ independent 8-deep chains
+#pragma unroll
+            for (int j = 0; j < BJ; ++j)
+#pragma unroll
+                for (int e = 0; e < BE; ++e)
+                    acc[j] = secular_term_acc(acc[j], dshift<KIND>(Dv[e], sig[j]), mm[j], W2[e]);
+        }
+
+        // ================= reduce this sweep's partial sums =================
+#pragma unroll
+        for (int j = 0; j < BJ; ++j) {
+            const double v = warp_allreduce(acc[j], OpSum());
+            if (lane == 0) sh.part[j][warp] = v;
+        }
+        __syncthreads();
+    }
+
+    // drain the prefetched tiles before the CTA (and its shared memory) goes away
+    if (tid == 0) {
+        for (long long gi = g; gi < g_issue; ++gi) mbar_wait(&sh.full[(int)(gi % BS)], (uint32_t)((gi / BS) & 1));
+    }
+}
+
+// =====================================================================================================
+// k_vec: eigenvector norm + normalised write, VJ consecutive eigenpairs per CTA
+constexpr int VT = 256, VW = VT / 32, VJ = 4;
+
+template <int KIND>
+__global__ void __launch_bounds__(VT, 2)
+k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_t cnt) {
+    __shared__ double red[VJ][VW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t N = P.N, Np = P.Np;
+    const double *__restrict__ D = P.D;
+    const double *__restrict__ W = P.w;
+    const int64_t c0 = (int64_t)blockIdx.x * VJ;
+
+    bool valid[VJ];
+    double sigma[VJ], mu[VJ], lambda[VJ];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < VJ; ++j) {
+        valid[j] = (c0 + j < cnt) && ks[c0 + j].flag == KS_DONE;
+        any = any || valid[j];
+        if (valid[j]) { sigma[j] = ks[c0 + j].sigma; mu[j] = ks[c0 + j].mu; lambda[j] = ks[c0 + j].lambda; }
+        else { sigma[j] = 0.0; mu[j] = -1.0e300; lambda[j] = 1.0; }
+    }
+    if (!any) return;
+
+    // ---- VNORM
+    double ss[VJ];
+#pragma unroll
+    for (int j = 0; j < VJ; ++j) ss[j] = 0.0;
+    for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * VT) {
+        const double2 d2 = ldg2(D + l0), w2 = ldg2(W + l0);
+        const double dv[2] = {d2.x, d2.y};
+        const double wv[2] = {w2.x, w2.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (l0 + h < N) {
+#pragma unroll
+                for (int j = 0; j < VJ; ++j) {
+                    const double v = __ddiv_rn(wv[h], __dadd_rn(dshift<KIND>(dv[h], sigma[j]), -mu[j]));
+                    ss[j] = __dadd_rn(ss[j], __dmul_rn(v, v));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < VJ; ++j) {
+        const double v = warp_allreduce(ss[j], OpSum());
+        if (lane == 0) red[j][warp] = v;
+    }
+    __syncthreads();
+    double inrm[VJ];
+#pragma unroll
+    for (int j = 0; j < VJ; ++j) {
+        double s = red[j][0];
+        for (int w = 1; w < VW; ++w) s = __dadd_rn(s, red[j][w]);
+        if (KIND != KIND_DPR1) s = __dadd_rn(s, 1.0);
+        inrm[j] = __ddiv_rn(1.0, sqrt(s));
+    }
+
+    // ---- VWRITE
+    const int64_t *umap = O.rowmap_u;
+    const int64_t *vmap = (KIND == KIND_HALF) ? O.rowmap_v : O.rowmap_u;
+    double *ucol[VJ], *vcol[VJ];
+#pragma unroll
+    for (int j = 0; j < VJ; ++j) {
+        const int64_t k = kbase + c0 + j;
+        const int64_t colidx = (valid[j] && umap) ? umap[k - 1] : c0 + j;
+        ucol[j] = (valid[j] && O.U) ? O.U + colidx * O.ldu : nullptr;
+        vcol[j] = (KIND == KIND_HALF && valid[j] && O.V) ? O.V + colidx * O.ldv : nullptr;
+    }
+    for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * VT) {
+        if (l0 >= N) break;
+        const double2 d2 = ldg2(D + l0), w2 = ldg2(W + l0);
+        const double dv[2] = {d2.x, d2.y};
+        const double wv[2] = {w2.x, w2.y};
+        double rs[2] = {1.0, 1.0};
+        if (KIND == KIND_HALF && O.rowscale_v) {
+            rs[0] = O.rowscale_v[l0];
+            if (l0 + 1 < N) rs[1] = O.rowscale_v[l0 + 1];
+        }
+#pragma unroll
+        for (int j = 0; j < VJ; ++j) {
+            double *const vec = (KIND == KIND_HALF) ? vcol[j] : ucol[j];
+            double v[2], vo[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                v[h] = __dmul_rn(__ddiv_rn(wv[h], __dadd_rn(dshift<KIND>(dv[h], sigma[j]), -mu[j])), inrm[j]);
+                vo[h] = (KIND == KIND_HALF && O.rowscale_v) ? __dmul_rn(v[h], rs[h]) : v[h];
+            }
+            if (vec) {
+                if (!vmap && l0 + 1 < N && ((reinterpret_cast<uintptr_t>(vec + l0) & 15) == 0)) {
+                    *reinterpret_cast<double2 *>(vec + l0) = make_double2(vo[0], vo[1]);
+                } else {
+                    vec[vmap ? vmap[l0] : l0] = vo[0];
+                    if (l0 + 1 < N) vec[vmap ? vmap[l0 + 1] : l0 + 1] = vo[1];
+                }
+            }
+            if (KIND == KIND_HALF && ucol[j]) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (l0 + h < N) ucol[j][umap ? umap[l0 + h] : l0 + h] = __ddiv_rn(__dmul_rn(lambda[j], v[h]), dv[h]);
+            }
+        }
+    }
+    if (KIND != KIND_DPR1 && tid < VJ) {
+#pragma unroll
+        for (int j = 0; j < VJ; ++j) {
+            if (j != tid || !valid[j]) continue;
+            double *const vec = (KIND == KIND_HALF) ? vcol[j] : ucol[j];
+            const double vt = __dmul_rn(-1.0, inrm[j]);
+            if (vec) vec[vmap ? vmap[N] : N] = vt;
+            if (KIND == KIND_HALF && ucol[j] && P.has_tip) ucol[j][umap ? umap[N] : N] = __ddiv_rn(__dmul_rn(P.ztip, vt), lambda[j]);
+        }
+    }
+}
+
+// =====================================================================================================
+inline int configure_pipe_kernels() {
+    const int smem = (int)sizeof(BisectShared);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_bisect<KIND_ARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_bisect<KIND_DPR1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_bisect<KIND_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)e;
+    return 0;
+}
+
+// P.D / P.w / P.w2 must be padded to P.Np, a multiple of TILE_POLES (see run_solver in ah_api.cu).
+inline int launch_prep(int kind, const Problem &P, KState *ks, int64_t kbase, int64_t cnt, int64_t *dlist,
+                       unsigned long long *dcount, cudaStream_t st) {
+    const int grid = (int)((cnt + PJ - 1) / PJ);
+    switch (kind) {
+        case KIND_ARROW: k_prep<KIND_ARROW><<<grid, PT, 0, st>>>(P, ks, kbase, cnt, dlist, dcount); break;
+        case KIND_DPR1: k_prep<KIND_DPR1><<<grid, PT, 0, st>>>(P, ks, kbase, cnt, dlist, dcount); break;
+        default: k_prep<KIND_HALF><<<grid, PT, 0, st>>>(P, ks, kbase, cnt, dlist, dcount); break;
+    }
+    return (int)cudaGetLastError();
+}
+inline int launch_bisect(int kind, const Problem &P, const Outputs &O, KState *ks, int64_t kbase, int64_t cnt,
+                         int64_t *dlist, unsigned long long *dcount, int sm_count, cudaStream_t st) {
+    const int smem = (int)sizeof(BisectShared);
+    // one CTA per SM, but never more CTAs than there are groups of BJ eigenpairs
+    const int64_t want = (cnt + BJ - 1) / BJ;
+    const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
+    switch (kind) {
+        case KIND_ARROW: k_bisect<KIND_ARROW><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, dcount); break;
+        case KIND_DPR1: k_bisect<KIND_DPR1><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, dcount); break;
+        default: k_bisect<KIND_HALF><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, dcount); break;
+    }
+    return (int)cudaGetLastError();
+}
+inline int launch_vec(int kind, const Problem &P, const Outputs &O, const KState *ks, int64_t kbase, int64_t cnt,
+                      cudaStream_t st) {
+    const int grid = (int)((cnt + VJ - 1) / VJ);
+    switch (kind) {
+        case KIND_ARROW: k_vec<KIND_ARROW><<<grid, VT, 0, st>>>(P, O, ks, kbase, cnt); break;
+        case KIND_DPR1: k_vec<KIND_DPR1><<<grid, VT, 0, st>>>(P, O, ks, kbase, cnt); break;
+        default: k_vec<KIND_HALF><<<grid, VT, 0, st>>>(P, O, ks, kbase, cnt); break;
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ah

@@ -226,7 +226,7 @@ def run_ours(args):
     N = n - 1
     fast = res.steps <= 80            # eigenpairs finished by the fast path (Remedy-3 ones take a 2nd bisection)
     n_fast = res.stats["n_fast"]
-    terms_fast = float((res.steps[fast].astype(np.float64) + 4.0).sum()) * N   # SHIFT+INV+S*BISECT+VNORM+VWRITE sweeps
+    terms_fast = float(res.steps[fast].astype(np.float64).sum()) * N   # k_bisect: one sweep of N secular terms per bisection step
     t_main = main_ms / args.steps * 1e-3
     instr_rate = FP64_INSTR_PER_TERM * terms_fast / t_main / 1e9       # G lane-instructions/s
     achieved_tf = 2.0 * instr_rate / 1e3
@@ -239,11 +239,11 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_achieved = cnt * n * 8 / t_main / 1e9
     roofline = {
-        "bound": "fp64", "kernel": "k_fast<SymArrow>", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "bound": "fp64", "kernel": "k_bisect<SymArrow>", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": achieved_tf / peak_tf, "traffic": None,
-        "how": "FP64-pipe lane-instructions x2 (FMA-equivalent); 7 per secular term x (steps_k+4) N terms per "
-               "fast-path eigenpair / mean k_fast duration; peak = dependent-free DFMA burst measured live "
-               "(MEASURED_PEAKS.json has no FP64 entry)",
+        "how": "FP64-pipe lane-instructions x2 (FMA-equivalent); 7 per secular term x steps_k x N terms per "
+               "fast-path eigenpair / mean k_bisect duration (CUDA events around the launch, inside the timed "
+               "region); peak = dependent-free DFMA burst measured live (MEASURED_PEAKS.json has no FP64 entry)",
         "terms_per_launch": terms_fast, "kernel_ms": t_main * 1e3, "fast_eigenpairs": int(n_fast),
         "hbm_store": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                       "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
@@ -299,7 +299,9 @@ def run_ours(args):
             "config": {"workload": f"SymArrow n={n} full eigen(), GenSymArrow-like rng(421), ordered, arrow top last",
                        "parallelism": f"k-range x{world}", "U": "device-resident, column blocks per rank",
                        "l2": "256 MB flush write before every step; the step itself streams out n^2*8 bytes >> L2",
-                       "kernel_ms_per_step_rank0": kern_ms / args.steps, "n_full_rank0": int(res.stats["n_full"]),
+                       "kernel_ms_per_step_rank0": kern_ms / args.steps,
+                       "kernel_ms_breakdown_rank0": {k: res.stats[k] for k in ("prep_ms", "bisect_ms", "vec_ms", "full_ms")},
+                       "n_full_rank0": int(res.stats["n_full"]),
                        "total_steps_rank0": int(res.stats["total_steps"])},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
             "cpu_baseline": cpu,

@@ -90,13 +90,14 @@ typedef struct ah_result {
 /* timing + accounting of the last compute call on a context */
 typedef struct ah_stats {
     double  kernel_ms;        /* device time of all kernels of the call (CUDA events on the context stream) */
-    double  main_kernel_ms;   /* device time of the fast-path kernel alone */
+    double  main_kernel_ms;   /* device time of the dominant kernel (k_bisect) alone */
     double  h2d_ms, d2h_ms;   /* host<->device copies issued by the call */
     int64_t launches;         /* number of kernels launched by the call */
-    int64_t n_fast;           /* eigenpairs finished by the fast-path kernel */
+    int64_t n_fast;           /* eigenpairs finished by the fast-path kernels (k_prep -> k_bisect -> k_vec) */
     int64_t n_full;           /* eigenpairs routed to the full (Remedy / double-double) kernel */
     int64_t total_steps;      /* sum of bisection steps */
     int64_t h2d_bytes, d2h_bytes;
+    double  prep_ms, bisect_ms, vec_ms, full_ms;   /* per-kernel device time: k_prep, k_bisect, k_vec, k_full */
 } ah_stats;
 
 /* ---- context ---------------------------------------------------------------------------------- */

@@ -94,7 +94,11 @@ def compare_range(gpu, orc, hi=None, *, lam_tol=10.0, vec_tol=100.0, k_tol=1e-9,
         fin = np.isfinite(o) & (o != 0)
         rel = np.abs(g[fin] - o[fin]) / np.abs(o[fin])
         out[name + "_rel"] = float(rel.max()) if rel.size else 0.0
-        assert out[name + "_rel"] <= k_tol, f"{name} differs: {out[name + '_rel']:.3e}"
+        # After Remedy 3 the shift sigma_1 = f(nu) itself carries the Knu-ulp uncertainty of the first nu
+        # (Knu > 1e3 there, up to 1e6 and more on graded data), so the re-shifted nu = 1/(lambda - sigma_1)
+        # and with it Knu and Krho legitimately differ at the 1e-9 level while lambda agrees.
+        allowed = np.where(orc.krho[ok][fin] != 0, 1e-6, k_tol) if name in ("knu", "krho") else k_tol
+        assert np.all(rel <= allowed), f"{name} differs: {out[name + '_rel']:.3e}"
         assert np.array_equal(g[~fin], o[~fin]) or not (~fin).any()
     for vname in ("U", "V"):
         G, O = getattr(gpu, vname, None), getattr(orc, vname, None)
