@@ -19,9 +19,9 @@
 // tile from shared memory into registers once and evaluates the term for all 8 slots from there, so
 // L2 and shared-memory traffic per term drop 8x and the FP64 pipe is the only busy unit.  One term is
 // 7 FP64-pipe instructions (DADD d, DFMA e=1-m d, DMUL t=d e, MUFU.RCP64H seed + 3 DFMA, DFMA accumulate).
-// The inner block is branch-free: the one pole per slot that must be skipped (the shift pole, d = 0) is
-// handled by its owner thread, which adds that pole's terms for the other slots on a rare side path and
-// then replaces its register copy by a harmless (pad pole, weight 0) pair.
+// The inner block is branch-free: the one pole per slot that must be skipped (the shift pole, d = 0)
+// poisons that slot's accumulator in exactly one thread, which saves the accumulator before the block
+// and redoes its four terms without the pole afterwards (a rare, warp-divergent side path).
 // A sweep ends with a fixed-order reduction (thread-sequential, xor-shuffle tree, warps 0..15); warp j
 // then advances slot j's bisection state, finalises a converged eigenpair (Knu test, Remedy-1 test) and
 // pulls the next k from a global counter, so all 8 slots stay busy until the work runs out.
@@ -291,6 +291,7 @@ struct BisectShared {
     alignas(16) double2 hot[BJ];   // (sigma, m) of every slot for the coming sweep
     double part[BJ][BW];
     long long skip[BJ];            // 0-based index of the slot's shift pole, -1: slot idle
+    double save[BJ];               // accumulator of slot j saved by the one thread that owns its shift pole
     BSlot slot[BJ];
 };
 
@@ -448,14 +449,11 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         __syncthreads();
 
         // ================= per-thread copies of the sweep parameters =================
-        double sig[BJ], mm[BJ];
         bool any_active = false;
         unsigned fixmask = 0;
         int fmin = 0x7fffffff, fmax_ = -1;
 #pragma unroll
         for (int j = 0; j < BJ; ++j) {
-            const double2 h = sh.hot[j];
-            sig[j] = h.x; mm[j] = h.y;
             const long long sk = sh.skip[j];
             any_active = any_active || (sk >= 0);
             if (sk >= 0) {
@@ -484,33 +482,44 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.empty[s]);
 
-            if (fixmask != 0 && tile >= fmin && tile <= fmax_) {
-                // rare: this thread holds the shift pole of some slot(s) in this tile.  Add the pole's
-                // terms for all OTHER slots here, then neutralise the register copy for the main block.
-                const long long base = (long long)tile * BTL;
+            // rare: this thread holds the shift pole (d = 0) of some slot(s) in this tile.  The main block
+            // below turns that slot's accumulator into NaN; save it here and redo the slot's four terms
+            // without the pole afterwards, in the same order as every other thread -> the summation order
+            // of a slot never depends on which other eigenpairs share the CTA (bitwise reproducible).
+            const bool fix = fixmask != 0 && tile >= fmin && tile <= fmax_;
+            if (fix) {
 #pragma unroll
-                for (int e = 0; e < BE; ++e) {
-                    const long long l = base + elem_offset(tid, e);
-                    bool hit = false;
-#pragma unroll
-                    for (int j = 0; j < BJ; ++j) hit = hit || (sh.skip[j] == l);
-                    if (hit) {
-#pragma unroll
-                        for (int j = 0; j < BJ; ++j)
-                            if (sh.skip[j] != l)
-                                acc[j] = secular_term_acc(acc[j], dshift<KIND>(Dv[e], sig[j]), mm[j], W2[e]);
-                        Dv[e] = P.pad;
-                        W2[e] = 0.0;
-                    }
-                }
+                for (int j = 0; j < BJ; ++j)
+                    if ((fixmask >> j) & 1u) sh.save[j] = acc[j];
             }
 
             // ---- the branch-free block: BE x BJ independent 8-deep chains
 #pragma unroll
-            for (int j = 0; j < BJ; ++j)
+            for (int j = 0; j < BJ; ++j) {
+                const double2 h = sh.hot[j];   // (sigma_j, m_j): broadcast LDS.128, reloaded per tile to save 32 registers
 #pragma unroll
                 for (int e = 0; e < BE; ++e)
-                    acc[j] = secular_term_acc(acc[j], dshift<KIND>(Dv[e], sig[j]), mm[j], W2[e]);
+                    acc[j] = secular_term_acc(acc[j], dshift<KIND>(Dv[e], h.x), h.y, W2[e]);
+            }
+
+            if (fix) {
+                const long long base = (long long)tile * BTL;
+#pragma unroll
+                for (int j = 0; j < BJ; ++j) {
+                    if ((fixmask >> j) & 1u) {
+                        const long long sk = sh.skip[j];
+                        if (sk / BTL == tile) {
+                            double a = sh.save[j];
+                            const double2 h = sh.hot[j];
+#pragma unroll
+                            for (int e = 0; e < BE; ++e)
+                                if (base + elem_offset(tid, e) != sk)
+                                    a = secular_term_acc(a, dshift<KIND>(Dv[e], h.x), h.y, W2[e]);
+                            acc[j] = a;
+                        }
+                    }
+                }
+            }
         }
 
         // ================= reduce this sweep's partial sums =================

@@ -238,7 +238,11 @@ def test_driver_halfarrow_svd(gpu_ctx, tip):
     A = ab.GenHalfArrow(60, tip, np.random.default_rng(4))
     S, info = ab.svd(A, ctx=gpu_ctx)
     O = oracle.svd_halfarrow(A.D, A.z)
-    assert np.max(np.abs(S.S - O.S) / np.abs(O.S)) <= 10 * EPS
+    H = oracle.svd_halfarrow(A.D, A.z, lib=oracle.get_lib_hi())
+    # 10 eps where the reference itself is determined that well; widened per singular value by its condition
+    # Knu (0.1 eps each) and by 3 x the reference's own summation noise (see helpers.compare_range)
+    bar = 10 + 0.1 * O.info.knu + 3 * np.abs(H.S - O.S) / np.abs(O.S) / EPS
+    assert np.all(np.abs(S.S - O.S) / np.abs(O.S) / EPS <= bar)
     assert np.max(np.abs(S.U - O.U)) <= 100 * EPS * max(1.0, np.max(np.abs(O.U))) * 10
     assert np.max(np.abs(S.Vt - O.Vt)) <= 100 * EPS
     M = A.dense()

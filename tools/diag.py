@@ -1,11 +1,14 @@
 #!/usr/bin/env python
 """Quick GPU diagnostic (not a test, not the bench): parity error statistics + kernel timings."""
+import os
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, "tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import arrowhead_b200 as ab
 import oracle
 from helpers import EPS, gen_symarrow, gen_symdpr1, gen_halfarrow

@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """Workload for ncu: a few full SymArrow solves with U resident on the device (no checks, no timing)."""
+import os
 import sys
 
 import numpy as np
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import arrowhead_b200 as ab
 
