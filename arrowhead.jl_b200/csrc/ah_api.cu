@@ -46,6 +46,7 @@ struct ah_ctx {
     void *hPinned = nullptr;  // pinned bounce buffer for the per-k outputs
     size_t hPinnedCap = 0;
     std::vector<double> hPadD, hPadW, hPadW2;
+    std::vector<cudaEvent_t> chunk_ev;   // 5 timing events per column block of the current call
     unsigned long long *hCounts = nullptr;  // pinned, 64 entries: per-block hand-over counts of the last call
 };
 
@@ -263,9 +264,16 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     int64_t n_full = 0;
     int nbuf = 0, n_count_reads = 0;
     for (int q = 0; q < 64; ++q) ctx->hCounts[q] = 0;
+    const int nchunks = (int)((cnt + chunk - 1) / chunk);
+    while ((int)ctx->chunk_ev.size() < 5 * nchunks) {
+        cudaEvent_t e;
+        AH_CUDA(cudaEventCreate(&e));
+        ctx->chunk_ev.push_back(e);
+    }
     for (int64_t c0 = 0; c0 < cnt; c0 += chunk, ++nbuf) {
         const int64_t cc = std::min(chunk, cnt - c0);
         const int slot = nbuf & 1;
+        cudaEvent_t *E = &ctx->chunk_ev[5 * (size_t)nbuf];   // start | prep done | bisect done | vec done | full done
         Outputs Oc = O;
         // outputs are indexed by k - kbase with kbase = k0 + c0; shift the SoA pointers accordingly
         Oc.lambda += c0; Oc.sind += c0; Oc.kb += c0; Oc.kz += c0; Oc.knu += c0; Oc.krho += c0;
@@ -284,23 +292,23 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         const int64_t kb = k0 + c0;
         int64_t *dlist = (int64_t *)ctx->dList.p;
         unsigned long long *dcount = (unsigned long long *)ctx->dCount.p;
-        AH_CUDA(cudaEventRecord(ctx->ev[2], st));
+        AH_CUDA(cudaEventRecord(E[0], st));
         if (ctx->mode == 0) {
             KState *ks = (KState *)ctx->dKs.p;
             AH_CUDA(cudaMemsetAsync(dcount, 0, 16, st));
             rc = ah::launch_prep(L.kind, P, ks, kb, cc, dlist, dcount, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_prep launch");
-            AH_CUDA(cudaEventRecord(ctx->ev[8], st));
+            AH_CUDA(cudaEventRecord(E[1], st));
             rc = ah::launch_bisect(L.kind, P, Oc, ks, kb, cc, dlist, dcount, ctx->sm_count, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect launch");
-            AH_CUDA(cudaEventRecord(ctx->ev[9], st));
+            AH_CUDA(cudaEventRecord(E[2], st));
             ctx->stats.launches += 2;
             if (wantU || wantV) {
                 rc = ah::launch_vec(L.kind, P, Oc, ks, kb, cc, st);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_vec launch");
                 ctx->stats.launches += 1;
             }
-            AH_CUDA(cudaEventRecord(ctx->ev[3], st));
+            AH_CUDA(cudaEventRecord(E[3], st));
             {
                 // the hand-over list is consumed straight from device memory; a few hundred CTAs cover the
                 // ~1 % of eigenpairs that take a Remedy / double-double branch
@@ -315,9 +323,9 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             }
             AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[nbuf & 63], dcount, 8, cudaMemcpyDeviceToHost, st));
             n_count_reads = std::min(nbuf + 1, 64);
-            AH_CUDA(cudaEventRecord(ctx->ev[4], st));
+            AH_CUDA(cudaEventRecord(E[4], st));
         } else {
-            AH_CUDA(cudaEventRecord(ctx->ev[3], st));
+            AH_CUDA(cudaEventRecord(E[3], st));
             const int grid = (int)std::min<int64_t>(cc, (int64_t)ctx->sm_count * 4);
             switch (L.kind) {
                 case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, st>>>(P, Oc, nullptr, kb, cc, nullptr); break;
@@ -327,7 +335,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             AH_CUDA(cudaGetLastError());
             ctx->stats.launches += 1;
             n_full += cc;
-            AH_CUDA(cudaEventRecord(ctx->ev[4], st));
+            AH_CUDA(cudaEventRecord(E[4], st));
         }
         if (staged) {
             // hand the finished block to the copy stream; the next block computes meanwhile
@@ -335,33 +343,23 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             AH_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[5], 0));
             char *sp = (char *)ctx->dStage[slot].p;
             if (hostU) {
-                AH_CUDA(cudaMemcpy2DAsync(out->U + c0 * out->ldu, out->ldu * 8, sp, L.nvec_u * 8, L.nvec_u * 8, cc,
-                                          cudaMemcpyDeviceToHost, ctx->copy_stream));
+                if (out->ldu == L.nvec_u)
+                    AH_CUDA(cudaMemcpyAsync(out->U + c0 * out->ldu, sp, (size_t)cc * L.nvec_u * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                else
+                    AH_CUDA(cudaMemcpy2DAsync(out->U + c0 * out->ldu, out->ldu * 8, sp, L.nvec_u * 8, L.nvec_u * 8, cc,
+                                              cudaMemcpyDeviceToHost, ctx->copy_stream));
                 sp += (size_t)cc * L.nvec_u * 8;
                 ctx->stats.d2h_bytes += cc * L.nvec_u * 8;
             }
             if (hostV) {
-                AH_CUDA(cudaMemcpy2DAsync(out->V + c0 * out->ldv, out->ldv * 8, sp, L.nvec_v * 8, L.nvec_v * 8, cc,
-                                          cudaMemcpyDeviceToHost, ctx->copy_stream));
+                if (out->ldv == L.nvec_v)
+                    AH_CUDA(cudaMemcpyAsync(out->V + c0 * out->ldv, sp, (size_t)cc * L.nvec_v * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                else
+                    AH_CUDA(cudaMemcpy2DAsync(out->V + c0 * out->ldv, out->ldv * 8, sp, L.nvec_v * 8, L.nvec_v * 8, cc,
+                                              cudaMemcpyDeviceToHost, ctx->copy_stream));
                 ctx->stats.d2h_bytes += cc * L.nvec_v * 8;
             }
             AH_CUDA(cudaEventRecord(ctx->ev_stage[slot], ctx->copy_stream));
-        }
-        // accumulate kernel times of this block (needs the events complete)
-        AH_CUDA(cudaEventSynchronize(ctx->ev[4]));
-        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
-        AH_CUDA(cudaEventElapsedTime(&t2, ctx->ev[2], ctx->ev[4]));
-        ms_all += t2;
-        AH_CUDA(cudaEventElapsedTime(&t3, ctx->ev[3], ctx->ev[4]));
-        ctx->stats.full_ms += t3;
-        if (ctx->mode == 0) {
-            AH_CUDA(cudaEventElapsedTime(&t1, ctx->ev[2], ctx->ev[8]));
-            ctx->stats.prep_ms += t1;
-            AH_CUDA(cudaEventElapsedTime(&t1, ctx->ev[8], ctx->ev[9]));
-            ctx->stats.bisect_ms += t1;
-            ms_main += t1;
-            AH_CUDA(cudaEventElapsedTime(&t1, ctx->ev[9], ctx->ev[3]));
-            ctx->stats.vec_ms += t1;
         }
     }
 
@@ -372,6 +370,23 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     AH_CUDA(cudaEventRecord(ctx->ev[7], st));
     AH_CUDA(cudaStreamSynchronize(st));
     if (staged) AH_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    for (int c = 0; c < nchunks; ++c) {   // kernel times of every column block
+        cudaEvent_t *E = &ctx->chunk_ev[5 * (size_t)c];
+        float t = 0.f;
+        AH_CUDA(cudaEventElapsedTime(&t, E[0], E[4]));
+        ms_all += t;
+        AH_CUDA(cudaEventElapsedTime(&t, E[3], E[4]));
+        ctx->stats.full_ms += t;
+        if (ctx->mode == 0) {
+            AH_CUDA(cudaEventElapsedTime(&t, E[0], E[1]));
+            ctx->stats.prep_ms += t;
+            AH_CUDA(cudaEventElapsedTime(&t, E[1], E[2]));
+            ctx->stats.bisect_ms += t;
+            ms_main += t;
+            AH_CUDA(cudaEventElapsedTime(&t, E[2], E[3]));
+            ctx->stats.vec_ms += t;
+        }
+    }
     ctx->stats.d2h_bytes += cnt * (8 * 7 + 4 * 2);
     {
         char *p = (char *)ctx->hPinned;
@@ -505,6 +520,7 @@ void ah_destroy(ah_ctx *ctx) {
     if (ctx->hCounts) cudaFreeHost(ctx->hCounts);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;

@@ -35,6 +35,12 @@ for n in (10, 1000, 4100):
               f"orth={np.linalg.norm(G.U.T@G.U-np.eye(n))/EPS/n:.2f}n*eps stats={G.stats}")
 ctx.set_mode(0)
 import torch
+hp = torch.empty(1 << 27, dtype=torch.float64, pin_memory=True)      # 1 GiB
+dv = torch.zeros(1 << 27, dtype=torch.float64, device="cuda")
+for rep in range(3):
+    torch.cuda.synchronize(); t0 = time.time(); hp.copy_(dv, non_blocking=True); torch.cuda.synchronize(); dt = time.time() - t0
+print(f"D2H pinned 1 GiB: {hp.numel()*8/dt/1e9:.1f} GB/s")
+del hp, dv
 for n in (8192, 32768):
     D, z, a = gen_symarrow(n, seed=421)
     U = torch.empty((n, n), dtype=torch.float64, device="cuda")
