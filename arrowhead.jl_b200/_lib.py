@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libarrowhead_b200.so")
+LIB_PATH = os.environ.get("ARROWHEAD_B200_LIB") or os.path.join(_PKG, "libarrowhead_b200.so")   # env: A/B builds only
 
 AH_MEM_HOST, AH_MEM_DEVICE = 0, 1
 ST_NU_INF, ST_NEEDS_BIGFLOAT, ST_POLE_RETURN, ST_REF_THROWS, ST_ITER_LIMIT = 1, 2, 4, 8, 16
@@ -37,6 +37,7 @@ class AhStats(C.Structure):
         ("launches", C.c_int64), ("n_fast", C.c_int64), ("n_full", C.c_int64), ("total_steps", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("prep_ms", C.c_double), ("bisect_ms", C.c_double), ("vec_ms", C.c_double), ("full_ms", C.c_double),
+        ("n_rem3", C.c_int64),
     ]
 
     def asdict(self):

@@ -42,7 +42,7 @@ struct ah_ctx {
     std::string err;
     int mode = 0;
     ah_stats stats = {};
-    DevBuf dD, dW, dW2, dKs, dZ, dMap1, dMap2, dScale, dOut, dList, dCount, dStage[2];
+    DevBuf dD, dW, dW2, dKs, dRList, dZ, dMap1, dMap2, dScale, dOut, dList, dCount, dStage[2];
     void *hPinned = nullptr;  // pinned bounce buffer for the per-k outputs
     size_t hPinnedCap = 0;
     std::vector<double> hPadD, hPadW, hPadW2;
@@ -242,6 +242,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     }
     if ((rc = ensure(ctx, ctx->dList, cnt * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dKs, (size_t)cnt * sizeof(ah::KState)))) return rc;
+    if ((rc = ensure(ctx, ctx->dRList, cnt * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dCount, 256))) return rc;
 
     // ---- eigenvector destination: device-resident, or host through a double-buffered staging area
@@ -295,12 +296,23 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         AH_CUDA(cudaEventRecord(E[0], st));
         if (ctx->mode == 0) {
             KState *ks = (KState *)ctx->dKs.p;
-            AH_CUDA(cudaMemsetAsync(dcount, 0, 16, st));
+            int64_t *rlist = (int64_t *)ctx->dRList.p;
+            AH_CUDA(cudaMemsetAsync(dcount, 0, 32, st));
             rc = ah::launch_prep(L.kind, P, ks, kb, cc, dlist, dcount, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_prep launch");
             AH_CUDA(cudaEventRecord(E[1], st));
-            rc = ah::launch_bisect(L.kind, P, Oc, ks, kb, cc, dlist, dcount, ctx->sm_count, st);
+            rc = ah::launch_bisect(L.kind, 0, P, Oc, ks, kb, cc, dlist, rlist, dcount, ctx->sm_count, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect launch");
+            // Remedy 3 on the fast path: re-shift (k_rem3_prep) and bisect again (round 1).  The list length
+            // lives on the device; the grids are sized for the ~1-3 % of eigenpairs that usually need it.
+            {
+                const int64_t guess = std::max<int64_t>(1, std::min<int64_t>(cc, cc / 32 + 64));
+                rc = ah::launch_rem3_prep(L.kind, P, ks, kb, guess, rlist, dlist, dcount, ctx->sm_count, st);
+                if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_rem3_prep launch");
+                rc = ah::launch_bisect(L.kind, 1, P, Oc, ks, kb, guess, dlist, rlist, dcount, ctx->sm_count, st);
+                if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect round 1 launch");
+                ctx->stats.launches += 2;
+            }
             AH_CUDA(cudaEventRecord(E[2], st));
             ctx->stats.launches += 2;
             if (wantU || wantV) {
@@ -321,8 +333,9 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                 AH_CUDA(cudaGetLastError());
                 ctx->stats.launches += 1;
             }
-            AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[nbuf & 63], dcount, 8, cudaMemcpyDeviceToHost, st));
-            n_count_reads = std::min(nbuf + 1, 64);
+            AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (nbuf & 31)], dcount, 8, cudaMemcpyDeviceToHost, st));
+            AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (nbuf & 31) + 1], dcount + 2, 8, cudaMemcpyDeviceToHost, st));
+            n_count_reads = std::min(nbuf + 1, 32);
             AH_CUDA(cudaEventRecord(E[4], st));
         } else {
             AH_CUDA(cudaEventRecord(E[3], st));
@@ -415,7 +428,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     ctx->stats.d2h_ms = td;
     ctx->stats.kernel_ms = ms_all;
     ctx->stats.main_kernel_ms = ms_main;
-    for (int q = 0; q < n_count_reads; ++q) n_full += (int64_t)ctx->hCounts[q];
+    for (int q = 0; q < n_count_reads; ++q) { n_full += (int64_t)ctx->hCounts[2 * q]; ctx->stats.n_rem3 += (int64_t)ctx->hCounts[2 * q + 1]; }
     ctx->stats.n_full = n_full;
     ctx->stats.n_fast = cnt - n_full;
     return AH_OK;
@@ -513,7 +526,7 @@ int ah_create(ah_ctx **pctx, int device) {
 void ah_destroy(ah_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf *b : {&ctx->dD, &ctx->dW, &ctx->dW2, &ctx->dKs, &ctx->dZ, &ctx->dMap1, &ctx->dMap2, &ctx->dScale, &ctx->dOut, &ctx->dList,
+    for (DevBuf *b : {&ctx->dD, &ctx->dW, &ctx->dW2, &ctx->dKs, &ctx->dRList, &ctx->dZ, &ctx->dMap1, &ctx->dMap2, &ctx->dScale, &ctx->dOut, &ctx->dList,
                       &ctx->dCount, &ctx->dStage[0], &ctx->dStage[1]})
         if (b->p) cudaFree(b->p);
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);

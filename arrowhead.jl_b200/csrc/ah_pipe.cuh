@@ -13,16 +13,16 @@
 // KState record; nothing of size N is ever materialised per eigenpair -- the inverse (D', z') of the
 // reference exists only as the formula  z'_l^2/(D'_l - m) = wz^2 * w_l^2 / (d_l (1 - m d_l)),  d_l = D_l - sigma.
 //
-// k_bisect is the hot kernel: persistent, one CTA of 16 warps per SM.  D and w^2 stream over and over
-// through a shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier); one tile =
-// 2048 poles.  A CTA bisects BJ = 8 eigenpairs ("slots") at once: each thread moves its 4 poles of the
+// k_bisect is the hot kernel: persistent, two CTAs of 8 warps per SM (while one CTA sits at its sweep
+// boundary the other keeps the FP64 pipe busy).  D and w^2 stream over and over through a shared-memory
+// ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier); one tile = 1024 poles.  A CTA bisects BJ = 8 eigenpairs ("slots") at once: each thread moves its 4 poles of the
 // tile from shared memory into registers once and evaluates the term for all 8 slots from there, so
 // L2 and shared-memory traffic per term drop 8x and the FP64 pipe is the only busy unit.  One term is
 // 7 FP64-pipe instructions (DADD d, DFMA e=1-m d, DMUL t=d e, MUFU.RCP64H seed + 3 DFMA, DFMA accumulate).
 // The inner block is branch-free: the one pole per slot that must be skipped (the shift pole, d = 0)
 // poisons that slot's accumulator in exactly one thread, which saves the accumulator before the block
 // and redoes its four terms without the pole afterwards (a rare, warp-divergent side path).
-// A sweep ends with a fixed-order reduction (thread-sequential, xor-shuffle tree, warps 0..15); warp j
+// A sweep ends with a fixed-order reduction (thread-sequential, xor-shuffle tree, warps 0..7); warp j
 // then advances slot j's bisection state, finalises a converged eigenpair (Knu test, Remedy-1 test) and
 // pulls the next k from a global counter, so all 8 slots stay busy until the work runs out.
 // Anything non-standard (double-double needed, Knu > tolnu -> Remedy 3, Remedy 1, |nu| = Inf) is
@@ -31,17 +31,23 @@
 #include "ah_device.cuh"
 #include "ah_full.cuh"
 
+#include <algorithm>
+
 namespace ah {
 
-enum : int { KS_READY = 0, KS_HANDOFF = 1, KS_DONE = 2 };
+enum : int { KS_READY = 0, KS_HANDOFF = 1, KS_DONE = 2, KS_REM3 = 3, KS_REM3_READY = 4 };
+// counters (unsigned long long[4]): [0] hand-over list length, [1] k_bisect round-0 work counter,
+//                                   [2] Remedy-3 list length,   [3] k_bisect round-1 work counter
 
 struct KState {   // 128 bytes per eigenpair
     double sigma, wz, b, left, right, nu1, Kb, Kz;   // written by k_prep
     double nu, mu, lambda, knu;                       // written by k_bisect
     int64_t i;                                        // shift index, 1-based
     int32_t sideR, flag, steps, pad_;
-    double spare_;
+    double krho;                                      // Remedy 3: K_rho of the re-shifted inverse
 };
+// Remedy-3 round (k_rem3_prep -> k_bisect round 1) re-uses the record: sigma := sigma_1 (HalfArrow: its
+// square root; the squared shift is parked in `lambda`), b := rho, left/right := DPR1 bracket, nu1 := new nu_1.
 static_assert(sizeof(KState) == 128, "KState layout");
 
 // ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------------
@@ -117,19 +123,23 @@ k_prep(Problem P, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *
         }
     }
 
-    // ---- SHIFT sweep (pads carry weight 0 and lie below every pole: their terms are exact zeros)
+    // ---- SHIFT sweep (pads carry weight 0 and lie below every pole: their terms are exact zeros).
+    // Only the sign of F(mid) is used (arrowhead3.jl:441) and the reference forms this sum with Julia's
+    // pairwise `sum`, so a <=1-ulp reciprocal (4 FP64-pipe instructions instead of ~10) changes nothing.
     double xs[PJ];
 #pragma unroll
     for (int j = 0; j < PJ; ++j) xs[j] = 0.0;
+    double2 d2n = ldg2(D + 2 * tid), w2n = ldg2(W + 2 * tid);
     for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * PT) {
-        const double2 d2 = ldg2(D + l0), w2 = ldg2(W + l0);
+        const double2 d2 = d2n, w2 = w2n;
+        if (l0 + 2 * PT < Np) { d2n = ldg2(D + l0 + 2 * PT); w2n = ldg2(W + l0 + 2 * PT); }   // prefetch the next pair
         const double dv[2] = {d2.x, d2.y};
         const double w2v[2] = {__dmul_rn(w2.x, w2.x), __dmul_rn(w2.y, w2.y)};
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int j = 0; j < PJ; ++j)
-                xs[j] = __dadd_rn(xs[j], __ddiv_rn(w2v[h], __dadd_rn(dshift<KIND>(dv[h], Dk[j]), -mid[j])));
+                xs[j] = __fma_rn(w2v[h], rcp_fast(__dadd_rn(dshift<KIND>(dv[h], Dk[j]), -mid[j])), xs[j]);
     }
 #pragma unroll
     for (int j = 0; j < PJ; ++j) {
@@ -164,12 +174,14 @@ k_prep(Problem P, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *
     }
     __syncthreads();
 
-    // ---- INV sweep: exact reference arithmetic for every entry of the inverse
+    // ---- INV sweep: the reference's formulas for every entry of the inverse, in its operation order
     double a0[PJ], a1[PJ], a2[PJ], a3[PJ], a4[PJ];
 #pragma unroll
     for (int j = 0; j < PJ; ++j) { a0[j] = 0.0; a1[j] = 0.0; a2[j] = 0.0; a3[j] = -INFINITY; a4[j] = 0.0; }
+    d2n = ldg2(D + 2 * tid); w2n = ldg2(W + 2 * tid);
     for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * PT) {
-        const double2 d2 = ldg2(D + l0), w2 = ldg2(W + l0);
+        const double2 d2 = d2n, w2 = w2n;
+        if (l0 + 2 * PT < Np) { d2n = ldg2(D + l0 + 2 * PT); w2n = ldg2(W + l0 + 2 * PT); }   // prefetch the next pair
         const double dv[2] = {d2.x, d2.y};
         const double wv[2] = {w2.x, w2.y};
 #pragma unroll
@@ -180,7 +192,7 @@ k_prep(Problem P, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *
 #pragma unroll
                 for (int j = 0; j < PJ; ++j) {
                     if (l != ii[j]) {
-                        const double Dp = __ddiv_rn(1.0, dshift<KIND>(dv[h], sigma[j]));
+                        const double Dp = rcp_fast(dshift<KIND>(dv[h], sigma[j]));   // feeds sums and maxima over N entries only
                         const double zp = __dmul_rn(__dmul_rn(-wv[h], Dp), wz[j]);
                         const double t = __dmul_rn(W2, Dp);
                         if (Dp > 0.0) a0[j] = __dadd_rn(a0[j], t); else a1[j] = __dadd_rn(a1[j], t);
@@ -249,7 +261,7 @@ k_prep(Problem P, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *
             S.Kb = __ddiv_rn(__dadd_rn(Ps, -Qs), fabs(PQ));
             if (KIND == KIND_DPR1) S.Kz = __dmul_rn(__dadd_rn(P.sumabs_w, -fabs(W[i0])), fabs(wzj));
             else S.Kz = __dmul_rn(P.maxabs_w, fabs(wzj));
-            S.nu = 0.0; S.mu = 0.0; S.lambda = 0.0; S.knu = 0.0; S.steps = 0; S.pad_ = 0; S.spare_ = 0.0;
+            S.nu = 0.0; S.mu = 0.0; S.lambda = 0.0; S.knu = 0.0; S.steps = 0; S.pad_ = 0; S.krho = 0.0;
             if (S.Kb < P.tau[0] || S.Kz < P.tau[1]) {
                 S.b = __dmul_rn(__dmul_rn(PQ, wzj), wzj);
                 S.nu1 = fmax(__dadd_rn(sabs, fabs(S.b)), nu1m);
@@ -268,13 +280,21 @@ k_prep(Problem P, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *
 
 // =====================================================================================================
 // k_bisect
-constexpr int BT = 512;          // threads per CTA
+#ifndef AH_BT
+#define AH_BT 256
+#endif
+#ifndef AH_BCTAS
+#define AH_BCTAS 2
+#endif
+constexpr int BT = AH_BT;        // threads per CTA
+constexpr int BCTAS = AH_BCTAS;  // CTAs per SM
 constexpr int BW = BT / 32;      // warps
 constexpr int BJ = 8;            // eigenpair slots per CTA
 constexpr int BE = 4;            // poles per thread per tile
 constexpr int BTL = BT * BE;     // poles per tile (2048)
 constexpr int BS = 4;            // ring stages
-constexpr int TILE_POLES = BTL;  // inputs are padded to a multiple of this
+constexpr int TILE_POLES = 2048; // inputs are padded to a multiple of this (a multiple of BTL)
+static_assert(TILE_POLES % BTL == 0, "tile size");
 
 enum : int { PH_FREE = 0, PH_BISECT, PH_DONE };
 
@@ -282,6 +302,7 @@ struct BSlot {   // cold per-slot state, touched by warp j only
     int64_t k, i;
     int phase, sideR, steps, pad_;
     double sigma, wz2, b, left, right, m, nu1, Kb, Kz;
+    double knu0, krho, sig2;   // round 1: first K_nu (HalfArrow keeps it), K_rho, squared shift (HalfArrow)
 };
 struct BisectShared {
     alignas(128) double tileD[BS][BTL];
@@ -290,7 +311,8 @@ struct BisectShared {
     alignas(8) unsigned long long empty[BS];
     alignas(16) double2 hot[BJ];   // (sigma, m) of every slot for the coming sweep
     double part[BJ][BW];
-    long long skip[BJ];            // 0-based index of the slot's shift pole, -1: slot idle
+    long long skip[BJ];            // 0-based index of the slot's shift pole, -1: none (idle slot, or Remedy-3 round)
+    int act[BJ];                   // slot is bisecting in the coming sweep
     double save[BJ];               // accumulator of slot j saved by the one thread that owns its shift pole
     BSlot slot[BJ];
 };
@@ -299,49 +321,84 @@ struct BisectShared {
 // consecutive lanes read consecutive 16-byte pairs -> conflict-free LDS.128.
 __device__ __forceinline__ int elem_offset(int t, int e) { return (e >> 1) * (2 * BT) + 2 * t + (e & 1); }
 
+// Remedy-1 trigger of the reference (arrowhead3.jl:526-534, arrowhead4.jl:400-408); the Remedy itself runs in k_full.
 template <int KIND>
+__device__ __forceinline__ bool wants_remedy1(const Problem &P, int64_t k, int64_t i, bool sideR, double mu, double lambda) {
+    const int64_t N = P.N, ii = i - 1;
+    const double Di = P.D[ii];
+    if (!(__ddiv_rn(__dadd_rn(fabs(Di), fabs(mu)), fabs(lambda)) > P.tau[4])) return false;
+    const bool c1 = (k == 1 && P.D[0] < 0.0);
+    const bool c2 = (KIND == KIND_ARROW) && (k == N + 1 && P.D[N - 1] > 0.0);
+    const bool c3 = (KIND == KIND_ARROW ? i < N : true) && !sideR && sign_jl(Di) + sign_jl(P.D[ii + 1 < N ? ii + 1 : ii]) == 0.0;
+    const bool c4 = (i > 1 && sideR && sign_jl(Di) + sign_jl(P.D[ii > 0 ? ii - 1 : 0]) == 0.0);
+    return c1 || c2 || c3 || c4;
+}
+
+// ROUND 0: nu of the inverse arrow (arrowhead3.jl:449-465).  Standard eigenpairs are finished here; K_nu > tolnu
+// goes to the Remedy-3 list (or, where the fast path has no round 1 for it, to k_full); the rest to k_full.
+// ROUND 1: nu of the re-shifted inverse (DPR1), arrowhead3.jl:497-511.
+template <int KIND, int ROUND>
 __device__ __forceinline__ void bisect_finalize(const Problem &P, const Outputs &O, KState *ks, BSlot &S, int64_t kbase,
-                                                int64_t *dlist, unsigned long long *dcount, int lane) {
+                                                int64_t *dlist, int64_t *rlist, unsigned long long *dcount, int lane) {
     const int64_t N = P.N;
-    const double nu = S.right;
+    double nu = S.right;
     const int64_t ii = S.i - 1;
-    const double Knu = __ddiv_rn(S.nu1, fabs(nu));
-    bool bail = !isfinite(nu);
-    if (KIND == KIND_HALF) bail = bail || !(Knu < P.tau[2]);
-    else bail = bail || (Knu > P.tau[2]);
-    double mu = 0.0, lambda = 0.0;
-    if (!bail) {
-        mu = __ddiv_rn(1.0, nu);
-        const double Di = P.D[ii];
-        if (KIND == KIND_HALF) {
-            lambda = sqrt(__dadd_rn(mu, __dmul_rn(S.sigma, S.sigma)));
-            bail = (S.k == N + 1) &&
-                   (__ddiv_rn(__dadd_rn(__dmul_rn(Di, Di), fabs(mu)), fabs(__dmul_rn(lambda, lambda))) > P.tau[4]);
+    double Knu = __ddiv_rn(S.nu1, fabs(nu));
+    enum { GO_DONE, GO_FULL, GO_REM3 } go = GO_DONE;
+    double mu = 0.0, lambda = 0.0, nu1 = S.nu1;
+    if (ROUND == 0) {
+        const bool big = (KIND == KIND_HALF) ? !(Knu < P.tau[2]) : (Knu > P.tau[2]);
+        if (!isfinite(nu)) go = GO_FULL;
+        else if (big) go = (KIND == KIND_HALF && S.k == N + 1) ? GO_FULL : GO_REM3;
+        else {
+            mu = __ddiv_rn(1.0, nu);
+            if (KIND == KIND_HALF) {
+                const double Di = P.D[ii];
+                lambda = sqrt(__dadd_rn(mu, __dmul_rn(S.sigma, S.sigma)));
+                if ((S.k == N + 1) &&
+                    (__ddiv_rn(__dadd_rn(__dmul_rn(Di, Di), fabs(mu)), fabs(__dmul_rn(lambda, lambda))) > P.tau[4])) go = GO_FULL;
+            } else {
+                lambda = __dadd_rn(mu, S.sigma);
+                if (wants_remedy1<KIND>(P, S.k, S.i, S.sideR != 0, mu, lambda)) go = GO_FULL;
+            }
+        }
+        if (go == GO_REM3) {   // sign conventions of arrowhead3.jl:469-471
+            nu = S.sideR ? fabs(nu) : -fabs(nu);
+            nu1 = -sign_jl(nu) * nu1;
+        }
+    } else {
+        if (KIND == KIND_ARROW && S.sideR && P.D[0] > 0.0 && nu < 0.0) go = GO_FULL;      // 'R' -> 'L' retry
+        if (KIND != KIND_HALF) {
+            if (isnan(Knu) || Knu > P.tau[2]) go = GO_FULL;                              // the while loop would go on
         } else {
-            lambda = __dadd_rn(mu, S.sigma);
-            if (__ddiv_rn(__dadd_rn(fabs(Di), fabs(mu)), fabs(lambda)) > P.tau[4]) {   // Remedy 1 wanted?
-                const int64_t k = S.k, i = S.i;
-                const bool c1 = (k == 1 && P.D[0] < 0.0);
-                const bool c2 = (KIND == KIND_ARROW) && (k == N + 1 && P.D[N - 1] > 0.0);
-                const bool c3 = (KIND == KIND_ARROW ? i < N : true) && !S.sideR &&
-                                sign_jl(Di) + sign_jl(P.D[ii + 1 < N ? ii + 1 : ii]) == 0.0;
-                const bool c4 = (i > 1 && S.sideR && sign_jl(Di) + sign_jl(P.D[ii > 0 ? ii - 1 : 0]) == 0.0);
-                bail = c1 || c2 || c3 || c4;
+            Knu = S.knu0;                                                                // arrowhead6.jl keeps the first K_nu
+        }
+        if (!isfinite(nu)) go = GO_FULL;
+        if (go == GO_DONE) {
+            mu = __ddiv_rn(1.0, nu);
+            if (KIND == KIND_HALF) lambda = sqrt(__dadd_rn(mu, S.sig2));
+            else {
+                lambda = __dadd_rn(mu, S.sigma);
+                if (wants_remedy1<KIND>(P, S.k, S.i, S.sideR != 0, mu, lambda)) go = GO_FULL;
             }
         }
     }
     if (lane == 0) {
         const int64_t col = S.k - kbase;
         KState &G = ks[col];
-        if (bail) {
+        if (go == GO_FULL) {
             G.flag = KS_HANDOFF;
             dlist[atomicAdd(dcount, 1ull)] = S.k;
+        } else if (go == GO_REM3) {
+            G.nu = nu; G.nu1 = nu1; G.knu = Knu; G.steps = S.steps;
+            G.flag = KS_REM3;
+            rlist[atomicAdd(dcount + 2, 1ull)] = S.k;
         } else {
             G.nu = nu; G.mu = mu; G.lambda = lambda; G.knu = Knu; G.steps = S.steps;
             G.flag = KS_DONE;
             O.lambda[col] = lambda;
             O.sind[col] = S.i;
-            O.kb[col] = S.Kb; O.kz[col] = S.Kz; O.knu[col] = Knu; O.krho[col] = 0.0;
+            O.kb[col] = S.Kb; O.kz[col] = S.Kz; O.knu[col] = Knu; O.krho[col] = (ROUND == 0) ? 0.0 : S.krho;
             O.qout[col] = 0;
             O.steps[col] = S.steps;
             O.status[col] = 0;
@@ -353,10 +410,10 @@ __device__ __forceinline__ bool bisect_converged(const BSlot &S) {
     return !((S.right - S.left) > 2.0 * kEps * fmax(fabs(S.left), fabs(S.right)));
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(BT, 1)
+template <int KIND, int ROUND>
+__global__ void __launch_bounds__(BT, BCTAS)
 k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *__restrict__ dlist,
-         unsigned long long *dcount) {
+         int64_t *__restrict__ rlist, unsigned long long *dcount) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BisectShared &sh = *reinterpret_cast<BisectShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -366,7 +423,8 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         for (int s = 0; s < BS; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], BW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < BJ) { sh.slot[tid].phase = PH_FREE; sh.skip[tid] = -1; sh.hot[tid] = make_double2(0.0, 0.0); }
+    if (tid < BJ) { sh.slot[tid].phase = PH_FREE; sh.skip[tid] = -1; sh.act[tid] = 0; sh.hot[tid] = make_double2(0.0, 0.0); }
+    if (ROUND == 1) cnt = (int64_t)dcount[2];   // round 1 works through the Remedy-3 list
     __syncthreads();
 
     long long g_issue = 0;   // tiles issued (thread 0 only)
@@ -395,13 +453,20 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                     sum = (lane & o) ? __dadd_rn(p, sum) : __dadd_rn(sum, p);
                 }
                 sum = __shfl_sync(0xffffffffu, sum, 0);
-                sum = __dmul_rn(sum, S.wz2);
                 const double m = S.m;
-                if (KIND != KIND_DPR1) sum = __dadd_rn(sum, __ddiv_rn(S.wz2, __dadd_rn(0.0, -m)));
-                const double F = __dadd_rn(__dadd_rn(S.b, -m), -sum);
+                bool goleft;
+                if (ROUND == 0) {
+                    sum = __dmul_rn(sum, S.wz2);
+                    if (KIND != KIND_DPR1) sum = __dadd_rn(sum, __ddiv_rn(S.wz2, __dadd_rn(0.0, -m)));
+                    goleft = __dadd_rn(__dadd_rn(S.b, -m), -sum) > 0.0;                  // arrowhead3.jl:696-701
+                } else {
+                    if (KIND != KIND_DPR1) sum = __dadd_rn(sum, __ddiv_rn(1.0, __dadd_rn(0.0, -m)));
+                    const double F = __dadd_rn(1.0, __dmul_rn(S.b, sum));                // b holds rho; arrowhead3.jl:736-740
+                    goleft = sign_jl(S.b) * F < 0.0;
+                }
                 __syncwarp();
                 if (lane == 0) {
-                    if (F > 0.0) S.left = m; else S.right = m;
+                    if (goleft) S.left = m; else S.right = m;
                     S.m = (S.left + S.right) / 2.0;
                     S.steps += 1;
                 }
@@ -411,15 +476,15 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             while (true) {
                 if (S.phase == PH_BISECT) {
                     if (!bisect_converged(S)) break;
-                    bisect_finalize<KIND>(P, O, ks, S, kbase, dlist, dcount, lane);
+                    bisect_finalize<KIND, ROUND>(P, O, ks, S, kbase, dlist, rlist, dcount, lane);
                     __syncwarp();
                     if (lane == 0) S.phase = PH_FREE;
                     __syncwarp();
                 }
                 if (S.phase == PH_DONE) break;
-                // PH_FREE: next eigenpair that k_prep left ready
+                // PH_FREE: next eigenpair that k_prep (round 1: k_rem3_prep) left ready
                 unsigned long long wi = 0;
-                if (lane == 0) wi = atomicAdd(dcount + 1, 1ull);
+                if (lane == 0) wi = atomicAdd(dcount + (ROUND == 0 ? 1 : 3), 1ull);
                 wi = __shfl_sync(0xffffffffu, wi, 0);
                 if ((int64_t)wi >= cnt) {
                     __syncwarp();
@@ -427,14 +492,17 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                     __syncwarp();
                     break;
                 }
-                const KState &G = ks[wi];
-                if (G.flag != KS_READY) continue;
+                const int64_t knew = (ROUND == 0) ? kbase + (int64_t)wi : rlist[wi];
+                const KState &G = ks[knew - kbase];
+                if (G.flag != (ROUND == 0 ? KS_READY : KS_REM3_READY)) continue;
                 __syncwarp();
                 if (lane == 0) {
-                    S.k = kbase + (int64_t)wi; S.i = G.i; S.sideR = G.sideR; S.steps = 0;
-                    S.sigma = G.sigma; S.wz2 = __dmul_rn(G.wz, G.wz); S.b = G.b;
+                    S.k = knew; S.i = G.i; S.sideR = G.sideR;
+                    S.sigma = G.sigma; S.b = G.b;
                     S.left = G.left; S.right = G.right; S.m = (G.left + G.right) / 2.0;
                     S.nu1 = G.nu1; S.Kb = G.Kb; S.Kz = G.Kz;
+                    if (ROUND == 0) { S.steps = 0; S.wz2 = __dmul_rn(G.wz, G.wz); }
+                    else { S.steps = G.steps; S.wz2 = 1.0; S.knu0 = G.knu; S.krho = G.krho; S.sig2 = G.lambda; }
                     S.phase = PH_BISECT;
                 }
                 __syncwarp();
@@ -442,27 +510,28 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             if (lane == 0) {
                 const bool act = S.phase == PH_BISECT;
                 sh.hot[warp] = act ? make_double2(S.sigma, S.m) : make_double2(0.0, 0.0);
-                sh.skip[warp] = act ? (long long)(S.i - 1) : -1;
+                sh.skip[warp] = (act && ROUND == 0) ? (long long)(S.i - 1) : -1;   // the re-shifted sigma_1 is not a pole
+                sh.act[warp] = act ? 1 : 0;
             }
         }
         first = false;
         __syncthreads();
 
         // ================= per-thread copies of the sweep parameters =================
-        bool any_active = false;
+        unsigned actmask = 0;
         unsigned fixmask = 0;
         int fmin = 0x7fffffff, fmax_ = -1;
 #pragma unroll
         for (int j = 0; j < BJ; ++j) {
             const long long sk = sh.skip[j];
-            any_active = any_active || (sk >= 0);
+            if (sh.act[j] != 0) actmask |= 1u << j;
             if (sk >= 0) {
                 const int t_i = (int)(sk / BTL);
                 const int owner = (int)(((sk % BTL) % (2 * BT)) >> 1);
                 if (owner == tid) { fixmask |= 1u << j; fmin = min(fmin, t_i); fmax_ = max(fmax_, t_i); }
             }
         }
-        if (!any_active) break;
+        if (actmask == 0) break;
         double acc[BJ];
 #pragma unroll
         for (int j = 0; j < BJ; ++j) acc[j] = 0.0;
@@ -493,7 +562,9 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                     if ((fixmask >> j) & 1u) sh.save[j] = acc[j];
             }
 
-            // ---- the branch-free block: BE x BJ independent 8-deep chains
+            // ---- the branch-free block: BE x BJ independent 8-deep chains.  (Idle slots -- end of the work list,
+            // Remedy-3 round -- are evaluated on dummy parameters: skipping them with CTA-uniform branches was
+            // measured and costs the full-occupancy case more than the tail gains.)
 #pragma unroll
             for (int j = 0; j < BJ; ++j) {
                 const double2 h = sh.hot[j];   // (sigma_j, m_j): broadcast LDS.128, reloaded per tile to save 32 registers
@@ -538,6 +609,65 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
 }
 
 // =====================================================================================================
+// k_rem3_prep: Remedy 3 (arrowhead3.jl:466-496, arrowhead4.jl:333-368, arrowhead6.jl:429-470), first half:
+// the new shift sigma_1 between the poles, the inverse there (a DPR1: only rho, K_rho and the bisection
+// bracket are formed, by inv_at_value of ah_full.cuh) -> KState for k_bisect round 1.  One CTA per listed
+// eigenpair (~1 % of all).  Anything beyond the plain binary64 branch (sigma_1 hits a pole, double-double rho)
+// is handed to k_full.
+constexpr int RT = 256;
+
+template <int KIND>
+__global__ void __launch_bounds__(RT)
+k_rem3_prep(Problem P, KState *__restrict__ ks, int64_t kbase, const int64_t *__restrict__ rlist, int64_t *__restrict__ dlist,
+            unsigned long long *dcount) {
+    __shared__ double red[2 * (RT / 32) + 2];
+    const int64_t nwork = (int64_t)dcount[2];
+    for (int64_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const int64_t k = rlist[wi];
+        KState &G = ks[k - kbase];
+        const double nu = G.nu, nu1 = G.nu1, sigma = G.sigma;
+        const bool sideR = G.sideR != 0;
+        double sigma1, shift;
+        if (KIND == KIND_HALF) {
+            sigma1 = __dadd_rn(__ddiv_rn(__dadd_rn(nu1, nu), __dmul_rn(__dmul_rn(2.0, nu), nu1)), __dmul_rn(sigma, sigma));
+            shift = sqrt(sigma1);
+        } else {
+            sigma1 = __dadd_rn(__ddiv_rn(__dadd_rn(nu1, nu), __dmul_rn(__dmul_rn(2.0, nu), nu1)), sigma);
+            shift = sigma1;
+        }
+        bool full = is_pole(P.D, P.N, shift) || !isfinite(shift);
+        InvValue R;
+        int status = 0;
+        if (!full) {   // CTA-uniform
+            inv_at_value<KIND, RT>(P, shift, P.tau[3], R, status, red);
+            full = (R.Qout != 0) || (status != 0) || !isfinite(R.rho);
+        }
+        if (threadIdx.x == 0) {
+            if (full) {
+                G.flag = KS_HANDOFF;
+                dlist[atomicAdd(dcount, 1ull)] = k;
+            } else {
+                const double ruu = __dmul_rn(R.rho, R.uu);
+                double left, right;   // bracket of bisect(::SymDPR1,side), arrowhead3.jl:722-726
+                if (R.rho > 0.0) {
+                    if (!sideR) { left = R.mn1; right = R.mn2; }
+                    else { left = R.mx1; right = __dadd_rn(R.mx1, ruu); }
+                } else {
+                    if (!sideR) { left = __dadd_rn(R.mn1, ruu); right = R.mn1; }
+                    else { left = R.mx2; right = R.mx1; }
+                }
+                G.sigma = shift; G.b = R.rho; G.krho = R.Krho;
+                G.left = left; G.right = right;
+                G.nu1 = __dadd_rn(R.maxabsD, __dmul_rn(fabs(R.rho), R.uu));
+                G.lambda = sigma1;
+                G.flag = KS_REM3_READY;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================================
 // k_vec: eigenvector norm + normalised write, VJ consecutive eigenpairs per CTA
 constexpr int VT = 256, VW = VT / 32, VJ = 4;
 
@@ -563,12 +693,14 @@ k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_
     }
     if (!any) return;
 
-    // ---- VNORM
+    // ---- VNORM (the norm is a sum over N entries: <=1-ulp reciprocal; the entries themselves are divided exactly below)
     double ss[VJ];
 #pragma unroll
     for (int j = 0; j < VJ; ++j) ss[j] = 0.0;
+    double2 d2n = ldg2(D + 2 * tid), w2n = ldg2(W + 2 * tid);
     for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * VT) {
-        const double2 d2 = ldg2(D + l0), w2 = ldg2(W + l0);
+        const double2 d2 = d2n, w2 = w2n;
+        if (l0 + 2 * VT < Np) { d2n = ldg2(D + l0 + 2 * VT); w2n = ldg2(W + l0 + 2 * VT); }   // prefetch the next pair
         const double dv[2] = {d2.x, d2.y};
         const double wv[2] = {w2.x, w2.y};
 #pragma unroll
@@ -576,8 +708,8 @@ k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_
             if (l0 + h < N) {
 #pragma unroll
                 for (int j = 0; j < VJ; ++j) {
-                    const double v = __ddiv_rn(wv[h], __dadd_rn(dshift<KIND>(dv[h], sigma[j]), -mu[j]));
-                    ss[j] = __dadd_rn(ss[j], __dmul_rn(v, v));
+                    const double v = __dmul_rn(wv[h], rcp_fast(__dadd_rn(dshift<KIND>(dv[h], sigma[j]), -mu[j])));
+                    ss[j] = __fma_rn(v, v, ss[j]);
                 }
             }
         }
@@ -608,9 +740,11 @@ k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_
         ucol[j] = (valid[j] && O.U) ? O.U + colidx * O.ldu : nullptr;
         vcol[j] = (KIND == KIND_HALF && valid[j] && O.V) ? O.V + colidx * O.ldv : nullptr;
     }
+    d2n = ldg2(D + 2 * tid); w2n = ldg2(W + 2 * tid);
     for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * VT) {
         if (l0 >= N) break;
-        const double2 d2 = ldg2(D + l0), w2 = ldg2(W + l0);
+        const double2 d2 = d2n, w2 = w2n;
+        if (l0 + 2 * VT < Np) { d2n = ldg2(D + l0 + 2 * VT); w2n = ldg2(W + l0 + 2 * VT); }
         const double dv[2] = {d2.x, d2.y};
         const double wv[2] = {w2.x, w2.y};
         double rs[2] = {1.0, 1.0};
@@ -658,9 +792,11 @@ k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_
 inline int configure_pipe_kernels() {
     const int smem = (int)sizeof(BisectShared);
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_bisect<KIND_ARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)e;
-    if ((e = cudaFuncSetAttribute(k_bisect<KIND_DPR1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)e;
-    if ((e = cudaFuncSetAttribute(k_bisect<KIND_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)e;
+#define AH_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)e
+    AH_SET_SMEM((k_bisect<KIND_ARROW, 0>)); AH_SET_SMEM((k_bisect<KIND_ARROW, 1>));
+    AH_SET_SMEM((k_bisect<KIND_DPR1, 0>));  AH_SET_SMEM((k_bisect<KIND_DPR1, 1>));
+    AH_SET_SMEM((k_bisect<KIND_HALF, 0>));  AH_SET_SMEM((k_bisect<KIND_HALF, 1>));
+#undef AH_SET_SMEM
     return 0;
 }
 
@@ -675,16 +811,36 @@ inline int launch_prep(int kind, const Problem &P, KState *ks, int64_t kbase, in
     }
     return (int)cudaGetLastError();
 }
-inline int launch_bisect(int kind, const Problem &P, const Outputs &O, KState *ks, int64_t kbase, int64_t cnt,
-                         int64_t *dlist, unsigned long long *dcount, int sm_count, cudaStream_t st) {
+// round 0: all READY eigenpairs of the block; round 1: the Remedy-3 list (its length is read on the device)
+inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O, KState *ks, int64_t kbase, int64_t cnt,
+                         int64_t *dlist, int64_t *rlist, unsigned long long *dcount, int sm_count, cudaStream_t st) {
     const int smem = (int)sizeof(BisectShared);
     // one CTA per SM, but never more CTAs than there are groups of BJ eigenpairs
     const int64_t want = (cnt + BJ - 1) / BJ;
-    const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
+    const int64_t cap = (int64_t)sm_count * BCTAS;
+    int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    if (round == 0) {
+        switch (kind) {
+            case KIND_ARROW: k_bisect<KIND_ARROW, 0><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
+            case KIND_DPR1: k_bisect<KIND_DPR1, 0><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
+            default: k_bisect<KIND_HALF, 0><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
+        }
+    } else {
+        switch (kind) {
+            case KIND_ARROW: k_bisect<KIND_ARROW, 1><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
+            case KIND_DPR1: k_bisect<KIND_DPR1, 1><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
+            default: k_bisect<KIND_HALF, 1><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
+        }
+    }
+    return (int)cudaGetLastError();
+}
+inline int launch_rem3_prep(int kind, const Problem &P, KState *ks, int64_t kbase, int64_t cnt, const int64_t *rlist,
+                            int64_t *dlist, unsigned long long *dcount, int sm_count, cudaStream_t st) {
+    const int grid = (int)std::min<int64_t>(cnt, (int64_t)sm_count * 4);
     switch (kind) {
-        case KIND_ARROW: k_bisect<KIND_ARROW><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, dcount); break;
-        case KIND_DPR1: k_bisect<KIND_DPR1><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, dcount); break;
-        default: k_bisect<KIND_HALF><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, dcount); break;
+        case KIND_ARROW: k_rem3_prep<KIND_ARROW><<<grid, RT, 0, st>>>(P, ks, kbase, rlist, dlist, dcount); break;
+        case KIND_DPR1: k_rem3_prep<KIND_DPR1><<<grid, RT, 0, st>>>(P, ks, kbase, rlist, dlist, dcount); break;
+        default: k_rem3_prep<KIND_HALF><<<grid, RT, 0, st>>>(P, ks, kbase, rlist, dlist, dcount); break;
     }
     return (int)cudaGetLastError();
 }

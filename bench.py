@@ -224,7 +224,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (k_fast) on this rank, from the same timed region
     N = n - 1
-    fast = res.steps <= 80            # eigenpairs finished by the fast path (Remedy-3 ones take a 2nd bisection)
+    fast = res.status == 0            # (k_full's few eigenpairs are included: their first bisection ran in k_bisect)
     n_fast = res.stats["n_fast"]
     terms_fast = float(res.steps[fast].astype(np.float64).sum()) * N   # k_bisect: one sweep of N secular terms per bisection step
     t_main = main_ms / args.steps * 1e-3
@@ -239,7 +239,7 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_achieved = cnt * n * 8 / t_main / 1e9
     roofline = {
-        "bound": "fp64", "kernel": "k_bisect<SymArrow>", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "bound": "fp64", "kernel": "k_bisect<SymArrow> (round 0 + Remedy-3 round 1)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": achieved_tf / peak_tf, "traffic": None,
         "how": "FP64-pipe lane-instructions x2 (FMA-equivalent); 7 per secular term x steps_k x N terms per "
                "fast-path eigenpair / mean k_bisect duration (CUDA events around the launch, inside the timed "
@@ -301,7 +301,7 @@ def run_ours(args):
                        "l2": "256 MB flush write before every step; the step itself streams out n^2*8 bytes >> L2",
                        "kernel_ms_per_step_rank0": kern_ms / args.steps,
                        "kernel_ms_breakdown_rank0": {k: res.stats[k] for k in ("prep_ms", "bisect_ms", "vec_ms", "full_ms")},
-                       "n_full_rank0": int(res.stats["n_full"]),
+                       "n_full_rank0": int(res.stats["n_full"]), "n_rem3_rank0": int(res.stats["n_rem3"]),
                        "total_steps_rank0": int(res.stats["total_steps"])},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
             "cpu_baseline": cpu,

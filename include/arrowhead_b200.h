@@ -97,7 +97,8 @@ typedef struct ah_stats {
     int64_t n_full;           /* eigenpairs routed to the full (Remedy / double-double) kernel */
     int64_t total_steps;      /* sum of bisection steps */
     int64_t h2d_bytes, d2h_bytes;
-    double  prep_ms, bisect_ms, vec_ms, full_ms;   /* per-kernel device time: k_prep, k_bisect, k_vec, k_full */
+    double  prep_ms, bisect_ms, vec_ms, full_ms;   /* per-kernel device time: k_prep, k_bisect (+ Remedy-3 round), k_vec, k_full */
+    int64_t n_rem3;           /* eigenpairs that took the Remedy-3 round of the fast path (counted in n_fast) */
 } ah_stats;
 
 /* ---- context ---------------------------------------------------------------------------------- */

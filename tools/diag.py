@@ -51,5 +51,5 @@ for n in (8192, 32768):
         s = G.stats
         terms = (G.steps.sum() + 4.0 * n) * (n - 1)
         print(f"n={n} rep={rep} wall={dt*1e3:.1f} ms kernel={s['kernel_ms']:.2f} ms main={s['main_kernel_ms']:.2f} ms "
-              f"prep={s['prep_ms']:.2f} vec={s['vec_ms']:.2f} full={s['full_ms']:.2f} n_full={s['n_full']} eigenpairs/s={n/(s['kernel_ms']*1e-3):.3e} terms/s={terms/(s['kernel_ms']*1e-3):.3e} "
+              f"prep={s['prep_ms']:.2f} vec={s['vec_ms']:.2f} full={s['full_ms']:.2f} n_full={s['n_full']} n_rem3={s['n_rem3']} eigenpairs/s={n/(s['kernel_ms']*1e-3):.3e} terms/s={terms/(s['kernel_ms']*1e-3):.3e} "
               f"fp64 instr/s (7/term)={7*terms/(s['kernel_ms']*1e-3)/1e9:.0f} G")
