@@ -306,7 +306,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             // Remedy 3 on the fast path: re-shift (k_rem3_prep) and bisect again (round 1).  The list length
             // lives on the device; the grids are sized for the ~1-3 % of eigenpairs that usually need it.
             {
-                const int64_t guess = std::max<int64_t>(1, std::min<int64_t>(cc, cc / 32 + 64));
+                const int64_t guess = std::max<int64_t>(1, std::min<int64_t>(cc, (int64_t)ctx->sm_count * 2 * ah::BJ));   // full grid; idle slots are skipped
                 rc = ah::launch_rem3_prep(L.kind, P, ks, kb, guess, rlist, dlist, dcount, ctx->sm_count, st);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_rem3_prep launch");
                 rc = ah::launch_bisect(L.kind, 1, P, Oc, ks, kb, guess, dlist, rlist, dcount, ctx->sm_count, st);
