@@ -49,6 +49,7 @@ EXPORTS = [
     "ah_symarrow_eigen", "ah_symdpr1_eigen", "ah_halfarrow_svd",
     "ah_device_malloc", "ah_device_free", "ah_host_alloc_pinned", "ah_host_free_pinned",
     "ah_memcpy_d2h", "ah_memcpy_h2d", "ah_set_identity", "ah_apply_givens_rows", "ah_gather_permuted",
+    "ah_scale_rows_phase",
     "ah_measure_fp64_peak", "ah_measure_store_bw",
 ]
 
@@ -88,6 +89,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ah_set_identity.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64]
     lib.ah_apply_givens_rows.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double]
     lib.ah_gather_permuted.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, _i64p, C.c_int64, _i64p, C.c_int64]
+    lib.ah_scale_rows_phase.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, _dp, C.c_int, C.c_int64, C.c_int64]
     lib.ah_measure_fp64_peak.argtypes = [vp, _dp, _dp]
     lib.ah_measure_store_bw.argtypes = [vp, C.c_int64, _dp]
     for name in EXPORTS:
@@ -237,6 +239,11 @@ class Context:
         rows = np.ascontiguousarray(rows, np.int64); cols = np.ascontiguousarray(cols, np.int64)
         self._check(self.lib.ah_gather_permuted(self.handle, C.c_void_p(int(dst_dev)), ld_dst, C.c_void_p(int(src_dev)),
                                                 ld_src, _ptr(rows, _i64p), rows.size, _ptr(cols, _i64p), cols.size))
+
+    def scale_rows_phase(self, dst_dev, ld_dst, src_dev, ld_src, phase, nrows, ncols):
+        phase = np.ascontiguousarray(phase, np.float64)
+        self._check(self.lib.ah_scale_rows_phase(self.handle, C.c_void_p(int(dst_dev)), ld_dst, C.c_void_p(int(src_dev)),
+                                                 ld_src, _ptr(phase, _dp), int(phase.shape[1]), nrows, ncols))
 
     def memcpy_d2h(self, dst: np.ndarray, src_dev, nbytes):
         self._check(self.lib.ah_memcpy_d2h(self.handle, dst.ctypes.data_as(C.c_void_p), C.c_void_p(int(src_dev)), nbytes))

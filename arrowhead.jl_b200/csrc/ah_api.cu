@@ -465,6 +465,22 @@ __global__ void k_gather(double *dst, int64_t ldd, const double *src, int64_t ld
         dst[c * ldd + r] = src[cols[c] * lds + rows[r]];
     }
 }
+template <int NC>
+__global__ void k_scale_rows_phase(double *dst, int64_t ldd, const double *__restrict__ src, int64_t lds,
+                                   const double *__restrict__ phase, int64_t nrows, int64_t ncols) {
+    const int64_t total = nrows * ncols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / nrows, r = idx - c * nrows;
+        const double v = src[c * lds + r];
+        double *o = dst + (c * ldd + r) * NC;
+        if (NC == 2) {
+            *reinterpret_cast<double2 *>(o) = make_double2(__dmul_rn(phase[2 * r], v), __dmul_rn(phase[2 * r + 1], v));
+        } else {
+            reinterpret_cast<double2 *>(o)[0] = make_double2(__dmul_rn(phase[4 * r], v), __dmul_rn(phase[4 * r + 1], v));
+            reinterpret_cast<double2 *>(o)[1] = make_double2(__dmul_rn(phase[4 * r + 2], v), __dmul_rn(phase[4 * r + 3], v));
+        }
+    }
+}
 __global__ void k_dfma_burst(double *out, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-9, x1 = x0 + 1e-3, x2 = x0 + 2e-3, x3 = x0 + 3e-3;
     double x4 = x0 + 4e-3, x5 = x0 + 5e-3, x6 = x0 + 6e-3, x7 = x0 + 7e-3;
@@ -687,6 +703,22 @@ int ah_gather_permuted(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const doubl
     AH_CUDA(cudaMemcpyAsync(ctx->dMap2.p, cols, ncols * 8, cudaMemcpyHostToDevice, ctx->stream));
     k_gather<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const int64_t *)ctx->dMap1.p, nrows,
                                                           (const int64_t *)ctx->dMap2.p, ncols);
+    AH_CUDA(cudaGetLastError());
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return AH_OK;
+}
+
+int ah_scale_rows_phase(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src,
+                        const double *phase, int ncomp, int64_t nrows, int64_t ncols) {
+    if (!ctx || !dst_dev || !src_dev || !phase || (ncomp != 2 && ncomp != 4) || nrows < 1 || ncols < 1 || ld_dst < nrows || ld_src < nrows)
+        return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->dScale, (size_t)nrows * ncomp * 8))) return rc;
+    AH_CUDA(cudaMemcpyAsync(ctx->dScale.p, phase, (size_t)nrows * ncomp * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = ctx->sm_count * 8;
+    if (ncomp == 2) k_scale_rows_phase<2><<<grid, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const double *)ctx->dScale.p, nrows, ncols);
+    else k_scale_rows_phase<4><<<grid, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const double *)ctx->dScale.p, nrows, ncols);
     AH_CUDA(cudaGetLastError());
     AH_CUDA(cudaStreamSynchronize(ctx->stream));
     return AH_OK;

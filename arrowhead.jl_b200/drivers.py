@@ -22,7 +22,7 @@ from __future__ import annotations
 import numpy as np
 
 from ._lib import Context, get_context
-from .types import SVD, Eigen, HalfArrow, Info, SymArrow, SymDPR1
+from .types import SVD, Eigen, HalfArrow, HermArrow, HermDPR1, Info, SymArrow, SymDPR1
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -279,12 +279,78 @@ def svd_halfarrow(A: HalfArrow, tau=None, *, ctx: Context | None = None, vectors
     return SVD(Uo, S[es], Vt), out_info
 
 
+# ---------------------------------------------------------------------------------------------------
+# Hermitian wrappers (hermitian.jl:107-139): phase vector c = z./abs.(z), real solve, `Diagonal(c)*U`.
+def phase_split(zc: np.ndarray):
+    """c = z ./ abs.(z) and the real border real(conj(c).*z), component-wise as Julia evaluates them
+    (complex: abs = hypot; quaternion: abs = sqrt(s^2+v1^2+v2^2+v3^2), products summed left to right)."""
+    if zc.shape[1] == 2:
+        mod = np.hypot(zc[:, 0], zc[:, 1])
+    else:
+        mod = np.sqrt(((zc[:, 0] * zc[:, 0] + zc[:, 1] * zc[:, 1]) + zc[:, 2] * zc[:, 2]) + zc[:, 3] * zc[:, 3])
+    c = zc / mod[:, None]
+    zr = c[:, 0] * zc[:, 0] + c[:, 1] * zc[:, 1]
+    for q in range(2, zc.shape[1]):
+        zr = zr + c[:, q] * zc[:, q]
+    return c, zr
+
+
+def _hyper_to_host(M: np.ndarray, nrows: int, ncomp: int) -> np.ndarray:
+    """(nrows*ncomp, ncols) column-major real -> complex (nrows, ncols) or quaternion (nrows, ncols, 4)."""
+    ncols = M.shape[1]
+    T = np.ascontiguousarray(M.T).reshape(ncols, nrows, ncomp)
+    if ncomp == 2:
+        return np.ascontiguousarray((T[:, :, 0] + 1j * T[:, :, 1]).T)
+    return np.ascontiguousarray(np.transpose(T, (1, 0, 2)))
+
+
+def _apply_phase(ctx, Ereal, phase, vectors):
+    """Diagonal(c) * U.vectors as a device kernel (ah_scale_rows_phase): complex/quaternion entries interleaved."""
+    if Ereal is None:
+        return None
+    ncomp = phase.shape[1]
+    if isinstance(Ereal, np.ndarray):          # trivial cases the driver answers on the host (1x1, diagonal)
+        H = phase[:, None, :] * Ereal[:, :, None]
+        return H[:, :, 0] + 1j * H[:, :, 1] if ncomp == 2 else H
+    n, m = Ereal.nrows, Ereal.ncols
+    out = DeviceMatrix(ctx, n * ncomp, m)
+    ctx.scale_rows_phase(out.ptr, n, Ereal.ptr, Ereal.ld, phase, n, m)
+    Ereal.free()
+    if vectors == "device":
+        return out
+    host = _hyper_to_host(out.to_host(), n, ncomp)
+    out.free()
+    return host
+
+
+def eigen_hermarrow(A: HermArrow, tau=None, *, ctx: Context | None = None, vectors="host", **kw):
+    """eigen(A::HermArrow) (hermitian.jl:107-115) -> (Eigen(values, complex|quaternion vectors), Info)."""
+    ctx = ctx or get_context()
+    c, zr = phase_split(A.zc)
+    E, info = eigen_symarrow(SymArrow(A.D, zr, A.a, A.i), tau, ctx=ctx, vectors=None if vectors is None else "device", **kw)
+    one = np.zeros((1, A.ncomp)); one[0, 0] = 1.0
+    phase = np.concatenate([c[: A.i - 1], one, c[A.i - 1:]])          # insert!(c, A.i, one(T))
+    return Eigen(E.values, _apply_phase(ctx, E.vectors, phase, vectors)), info
+
+
+def eigen_hermdpr1(A: HermDPR1, tau=None, *, ctx: Context | None = None, vectors="host", **kw):
+    """eigen(A::HermDPR1) (hermitian.jl:131-139)."""
+    ctx = ctx or get_context()
+    c, ur = phase_split(A.uc)
+    E, info = eigen_symdpr1(SymDPR1(A.D, ur, A.r), tau, ctx=ctx, vectors=None if vectors is None else "device", **kw)
+    return Eigen(E.values, _apply_phase(ctx, E.vectors, c, vectors)), info
+
+
 def eigen(A, tau=None, **kw):
     """LinearAlgebra.eigen dispatch of the reference (arrowhead1.jl:2)."""
     if isinstance(A, SymArrow):
         return eigen_symarrow(A, tau, **kw)
     if isinstance(A, SymDPR1):
         return eigen_symdpr1(A, tau, **kw)
+    if isinstance(A, HermArrow):
+        return eigen_hermarrow(A, tau, **kw)
+    if isinstance(A, HermDPR1):
+        return eigen_hermdpr1(A, tau, **kw)
     raise TypeError(f"eigen: unsupported type {type(A).__name__}")
 
 

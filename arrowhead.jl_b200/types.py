@@ -99,6 +99,90 @@ class HalfArrow:
         return A
 
 
+def _as_hyper(z, ncomp=None):
+    """complex vector -> (n,2) float array; quaternion vectors are given as (n,4) [s, v1, v2, v3] arrays."""
+    z = np.asarray(z)
+    if np.iscomplexobj(z):
+        z = z.ravel()
+        return np.stack([z.real, z.imag], axis=1).astype(np.float64)
+    z = np.asarray(z, np.float64)
+    if z.ndim == 1:
+        return np.stack([z, np.zeros_like(z)], axis=1)
+    if z.ndim != 2 or z.shape[1] not in (2, 4):
+        raise ValueError("complex (n,) / (n,2) or quaternion (n,4) entries expected")
+    return z.copy()
+
+
+class HermArrow:
+    """Hermitian arrow [diag(D) z; z' a] with complex or quaternion border (hermitian.jl:9-14).
+    `z` is a complex vector or an (n,4) array of quaternion components; stored as (n, ncomp) reals."""
+
+    def __init__(self, D, z, a, i):
+        self.D = np.array(D, dtype=np.float64).ravel()
+        self.zc = _as_hyper(z)
+        if self.D.size != self.zc.shape[0]:
+            raise ValueError("HermArrow: D and z must have the same length")
+        self.a = float(a)
+        self.i = int(i)
+
+    @property
+    def ncomp(self):
+        return self.zc.shape[1]
+
+    @property
+    def z(self):
+        return self.zc[:, 0] + 1j * self.zc[:, 1] if self.ncomp == 2 else self.zc
+
+    def dense(self) -> np.ndarray:
+        """complex dense matrix (complex border only)"""
+        if self.ncomp != 2:
+            raise NotImplementedError("dense() of a quaternion matrix")
+        n = self.D.size + 1
+        t = self.i - 1
+        idx = np.array([r for r in range(n) if r != t], dtype=np.int64)
+        A = np.zeros((n, n), dtype=np.complex128)
+        A[idx, idx] = self.D
+        A[idx, t] = self.z
+        A[t, idx] = np.conj(self.z)
+        A[t, t] = self.a
+        return A
+
+
+class HermDPR1:
+    """diag(D) + r*u*u' with complex or quaternion u (hermitian.jl:47-51)."""
+
+    def __init__(self, D, u, r):
+        self.D = np.array(D, dtype=np.float64).ravel()
+        self.uc = _as_hyper(u)
+        if self.D.size != self.uc.shape[0]:
+            raise ValueError("HermDPR1: D and u must have the same length")
+        self.r = float(r)
+
+    @property
+    def ncomp(self):
+        return self.uc.shape[1]
+
+    @property
+    def u(self):
+        return self.uc[:, 0] + 1j * self.uc[:, 1] if self.ncomp == 2 else self.uc
+
+    def dense(self) -> np.ndarray:
+        if self.ncomp != 2:
+            raise NotImplementedError("dense() of a quaternion matrix")
+        return np.diag(self.D).astype(np.complex128) + self.r * np.outer(self.u, np.conj(self.u))
+
+
+def GenHermArrow(n: int, i: int, ncomp: int = 2, rng=None) -> HermArrow:
+    """GenHermArrow(n,i,T) (hermitian.jl:76-79): rand(T) has every component uniform in [0,1)."""
+    rng = np.random.default_rng() if rng is None else rng
+    return HermArrow(rng.random(n - 1), rng.random((n - 1, ncomp)), rng.random(), i)
+
+
+def GenHermDPR1(n: int, ncomp: int = 2, rng=None) -> HermDPR1:
+    rng = np.random.default_rng() if rng is None else rng
+    return HermDPR1(rng.random(n), rng.random((n, ncomp)), rng.random())
+
+
 def GenSymArrow(n: int, i: int, rng=None) -> SymArrow:
     rng = np.random.default_rng() if rng is None else rng
     return SymArrow(rng.random(n - 1), rng.random(n - 1), rng.random(), i)

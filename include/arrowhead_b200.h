@@ -144,6 +144,13 @@ int ah_apply_givens_rows(ah_ctx *ctx, double *U_dev, int64_t ld, int64_t ncols, 
 int ah_gather_permuted(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src,
                        const int64_t *rows, int64_t nrows, const int64_t *cols, int64_t ncols);
 
+/* Hermitian wrappers (src/hermitian.jl:107-115, 131-139: `Diagonal(c)*U.vectors`):
+ * dst[(c*ld_dst + r)*ncomp + q] = phase[r*ncomp + q] * src[c*ld_src + r], q < ncomp (2: complex, 4: quaternion).
+ * src is the real eigenvector matrix on the device, dst a device buffer of nrows*ncols*ncomp doubles
+ * (interleaved components = ComplexF64 / QuaternionF64 layout), phase a host array. */
+int ah_scale_rows_phase(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src,
+                        const double *phase, int ncomp, int64_t nrows, int64_t ncols);
+
 /* ---- measurement helpers (used by bench.py for the roofline denominators) ---------------------- */
 /* Dependent-free DFMA burst on every SM: returns FP64-pipe instruction issue rate in
  * 1e9 warp-lane-instructions/s (x2 = GFLOP/s) and the elapsed ms. */

@@ -13,6 +13,8 @@ from .lib import OracleLib, get_lib, get_lib_hi, build  # noqa: F401
 from .drivers import (  # noqa: F401
     eigen_symarrow,
     eigen_symdpr1,
+    eigen_hermarrow,
+    eigen_hermdpr1,
     svd_halfarrow,
     tdc,
     default_tau,

@@ -369,3 +369,39 @@ def tdc(dv, ev, lib=None, nthreads=0, rotation="reference"):
     W[:k, :] = U1 @ W[:k, :]
     W[k + 1:, :] = U2 @ W[k + 1:, :]
     return E.values, W
+
+
+# ------------------------------------------------------------------------------------------ Hermitian wrappers
+def _phase_split(zc):
+    """hermitian.jl:108-110 / 132-135: c = z./abs.(z); real border real(conj(c).*z) (components summed left to right)."""
+    zc = np.asarray(zc, np.float64)
+    if zc.shape[1] == 2:
+        mod = np.hypot(zc[:, 0], zc[:, 1])
+    else:
+        mod = np.sqrt(((zc[:, 0] * zc[:, 0] + zc[:, 1] * zc[:, 1]) + zc[:, 2] * zc[:, 2]) + zc[:, 3] * zc[:, 3])
+    c = zc / mod[:, None]
+    zr = c[:, 0] * zc[:, 0] + c[:, 1] * zc[:, 1]
+    for q in range(2, zc.shape[1]):
+        zr = zr + c[:, q] * zc[:, q]
+    return c, zr
+
+
+def _scale_rows(c, U):
+    H = c[:, None, :] * U[:, :, None]                      # Diagonal(c) * U, component by component
+    return H[:, :, 0] + 1j * H[:, :, 1] if c.shape[1] == 2 else H
+
+
+def eigen_hermarrow(D, zc, a, i, **kw) -> EigenResult:
+    """eigen(A::HermArrow), hermitian.jl:107-115.  zc: (n, 2|4) real components of the border."""
+    c, zr = _phase_split(zc)
+    E = eigen_symarrow(D, zr, a, i, **kw)
+    one = np.zeros((1, c.shape[1])); one[0, 0] = 1.0
+    phase = np.concatenate([c[: i - 1], one, c[i - 1:]])
+    return EigenResult(E.values, _scale_rows(phase, np.asarray(E.vectors)), E.info, E.perm, E.ref_throws)
+
+
+def eigen_hermdpr1(D, uc, r, **kw) -> EigenResult:
+    """eigen(A::HermDPR1), hermitian.jl:131-139."""
+    c, ur = _phase_split(uc)
+    E = eigen_symdpr1(D, ur, r, **kw)
+    return EigenResult(E.values, _scale_rows(c, np.asarray(E.vectors)), E.info, E.perm, E.ref_throws)
