@@ -49,7 +49,8 @@ EXPORTS = [
     "ah_symarrow_eigen", "ah_symdpr1_eigen", "ah_halfarrow_svd",
     "ah_device_malloc", "ah_device_free", "ah_host_alloc_pinned", "ah_host_free_pinned",
     "ah_memcpy_d2h", "ah_memcpy_h2d", "ah_set_identity", "ah_apply_givens_rows", "ah_gather_permuted",
-    "ah_scale_rows_phase",
+    "ah_scale_rows_phase", "ah_symarrow_eigen_batched", "ah_gather_elements", "ah_gather_permuted_batched",
+    "ah_copy2d_batched", "ah_dgemm_batched",
     "ah_measure_fp64_peak", "ah_measure_store_bw",
 ]
 
@@ -89,6 +90,13 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ah_set_identity.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64]
     lib.ah_apply_givens_rows.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double]
     lib.ah_gather_permuted.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, _i64p, C.c_int64, _i64p, C.c_int64]
+    u64p = C.POINTER(C.c_uint64)
+    lib.ah_symarrow_eigen_batched.argtypes = [vp, C.c_int64, C.c_int64, _dp, _dp, _dp, _dp, C.POINTER(AhResult), C.c_int64]
+    lib.ah_gather_elements.argtypes = [vp, vp, _i64p, C.c_int64, _dp]
+    lib.ah_gather_permuted_batched.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int64, _i64p, C.c_int64,
+                                               _i64p, C.c_int64]
+    lib.ah_copy2d_batched.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, u64p, C.c_int64, u64p, C.c_int64]
+    lib.ah_dgemm_batched.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, u64p, C.c_int64, u64p, C.c_int64, u64p, C.c_int64]
     lib.ah_scale_rows_phase.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, _dp, C.c_int, C.c_int64, C.c_int64]
     lib.ah_measure_fp64_peak.argtypes = [vp, _dp, _dp]
     lib.ah_measure_store_bw.argtypes = [vp, C.c_int64, _dp]
@@ -227,6 +235,46 @@ class Context:
         args = (C.c_int64(nd), C.c_int64(nz), _ptr(D, _dp), _ptr(z, _dp), _ptr(tau_a, _dp))
         return self._run(self.lib.ah_halfarrow_svd, args, k0, k1, nz, nd + 1, vectors, U_dev, ldu, V_dev, ldv, rowmap_u,
                          rowmap_v, rowscale_v)
+
+    # ---- batched primitives (tdc) -----------------------------------------------------------------
+    def symarrow_batched(self, D, z, a, tau=None, U_dev=None, ldu=0, ustride=0):
+        """nb ordered SymArrow problems with N poles each: D, z (nb, N), a (nb,) -> RangeResult with (nb*(N+1),) arrays."""
+        D = np.ascontiguousarray(D, np.float64); z = np.ascontiguousarray(z, np.float64); a = np.ascontiguousarray(a, np.float64)
+        nb, N = D.shape
+        tau_a = None if tau is None else np.ascontiguousarray(tau, np.float64)
+        res = RangeResult(1, nb * (N + 1))
+        r = AhResult()
+        res.fill(r)
+        if U_dev is not None:
+            r.U, r.ldu, r.U_mem = C.c_void_p(int(U_dev)), int(ldu), AH_MEM_DEVICE
+        self._check(self.lib.ah_symarrow_eigen_batched(self.handle, nb, N, _ptr(D, _dp), _ptr(z, _dp), _ptr(a, _dp), _ptr(tau_a, _dp),
+                                                       C.byref(r), int(ustride)))
+        res.stats = self.stats()
+        return res
+
+    def gather_elements(self, src_dev, idx):
+        idx = np.ascontiguousarray(idx, np.int64)
+        out = np.empty(idx.size)
+        self._check(self.lib.ah_gather_elements(self.handle, C.c_void_p(int(src_dev)), _ptr(idx, _i64p), idx.size, _ptr(out, _dp)))
+        return out
+
+    def gather_permuted_batched(self, dst_dev, dst_stride, ld_dst, src_dev, src_stride, ld_src, rows, cols):
+        rows = np.ascontiguousarray(rows, np.int64); cols = np.ascontiguousarray(cols, np.int64)
+        self._check(self.lib.ah_gather_permuted_batched(self.handle, rows.shape[0], C.c_void_p(int(dst_dev)), dst_stride, ld_dst,
+                                                        C.c_void_p(int(src_dev)), src_stride, ld_src, _ptr(rows, _i64p),
+                                                        rows.shape[1], _ptr(cols, _i64p), cols.shape[1]))
+
+    def copy2d_batched(self, nrows, ncols, dst_ptrs, ld_dst, src_ptrs, ld_src):
+        d = np.ascontiguousarray(dst_ptrs, np.uint64); s_ = np.ascontiguousarray(src_ptrs, np.uint64)
+        u64p = C.POINTER(C.c_uint64)
+        self._check(self.lib.ah_copy2d_batched(self.handle, d.size, nrows, ncols, d.ctypes.data_as(u64p), ld_dst,
+                                               s_.ctypes.data_as(u64p), ld_src))
+
+    def dgemm_batched(self, m, n, k, A_ptrs, lda, B_ptrs, ldb, C_ptrs, ldc):
+        A = np.ascontiguousarray(A_ptrs, np.uint64); B = np.ascontiguousarray(B_ptrs, np.uint64); Cc = np.ascontiguousarray(C_ptrs, np.uint64)
+        u64p = C.POINTER(C.c_uint64)
+        self._check(self.lib.ah_dgemm_batched(self.handle, A.size, m, n, k, A.ctypes.data_as(u64p), lda, B.ctypes.data_as(u64p), ldb,
+                                              Cc.ctypes.data_as(u64p), ldc))
 
     # ---- device utilities -------------------------------------------------------------------------
     def set_identity(self, U_dev, nrows, ncols, ld):

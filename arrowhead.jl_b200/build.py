@@ -14,7 +14,7 @@ OUT = os.path.join(_PKG, "libarrowhead_b200.so")
 # -fmad=false: the only FMAs in the binary are the explicit ones (secular term, two-product), so the
 # rest rounds like the reference's Julia code.  -lineinfo: ncu source pages map to these files.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-lcublas"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

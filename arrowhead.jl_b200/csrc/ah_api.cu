@@ -6,6 +6,7 @@
 // ah_fast.cuh / ah_full.cuh or fails.
 #include "../../include/arrowhead_b200.h"
 
+#include <cublas_v2.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -46,6 +47,8 @@ struct ah_ctx {
     void *hPinned = nullptr;  // pinned bounce buffer for the per-k outputs
     size_t hPinnedCap = 0;
     std::vector<double> hPadD, hPadW, hPadW2;
+    cublasHandle_t blas = nullptr;       // created on first use (ah_dgemm_batched)
+    DevBuf dPtrA, dPtrB, dPtrC, dIdx, dBatchA;
     std::vector<cudaEvent_t> chunk_ev;   // 5 timing events per column block of the current call
     unsigned long long *hCounts = nullptr;  // pinned, 64 entries: per-block hand-over counts of the last call
 };
@@ -465,6 +468,44 @@ __global__ void k_gather(double *dst, int64_t ldd, const double *src, int64_t ld
         dst[c * ldd + r] = src[cols[c] * lds + rows[r]];
     }
 }
+// nb problems of equal size in one launch: work item = (problem b, eigenpair k), one CTA each
+template <int KIND, int BT>
+__global__ void __launch_bounds__(BT) k_full_batched(ah::Problem P0, ah::Outputs O0, int64_t nb, const double *__restrict__ avals,
+                                                      const double *__restrict__ maxabs, int64_t ustride) {
+    __shared__ double red[2 * (BT / 32) + 2];
+    const int64_t per = P0.N + 1, total = nb * per;
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const int64_t b = w / per, k = w - b * per + 1;
+        ah::Problem P = P0;
+        P.D += b * P0.N; P.w += b * P0.N;
+        P.a = avals[b]; P.maxabs_w = maxabs[b];
+        ah::Outputs O = O0;
+        const int64_t o = b * per;
+        O.lambda += o; O.sind += o; O.kb += o; O.kz += o; O.knu += o; O.krho += o; O.qout += o; O.steps += o; O.status += o;
+        if (O0.U) O.U = O0.U + b * ustride;
+        ah::solve_full<KIND, BT>(P, O, k, k - 1, red);
+        __syncthreads();
+    }
+}
+__global__ void k_gather_elems(double *dst, const double *__restrict__ src, const int64_t *__restrict__ idx, int64_t count) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) dst[t] = src[idx[t]];
+}
+__global__ void k_gather_batched(double *dst, int64_t dstride, int64_t ldd, const double *__restrict__ src, int64_t sstride, int64_t lds,
+                                 const int64_t *__restrict__ rows, int64_t nrows, const int64_t *__restrict__ cols, int64_t ncols, int64_t nb) {
+    const int64_t per = nrows * ncols, total = per * nb;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / per, e = t - b * per, c = e / nrows, r = e - c * nrows;
+        dst[b * dstride + c * ldd + r] = src[b * sstride + cols[b * ncols + c] * lds + rows[b * nrows + r]];
+    }
+}
+__global__ void k_copy2d_batched(const uint64_t *__restrict__ dptr, int64_t ldd, const uint64_t *__restrict__ sptr, int64_t lds, int64_t nrows,
+                                 int64_t ncols, int64_t nb) {
+    const int64_t per = nrows * ncols, total = per * nb;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / per, e = t - b * per, c = e / nrows, r = e - c * nrows;
+        reinterpret_cast<double *>(dptr[b])[c * ldd + r] = reinterpret_cast<const double *>(sptr[b])[c * lds + r];
+    }
+}
 template <int NC>
 __global__ void k_scale_rows_phase(double *dst, int64_t ldd, const double *__restrict__ src, int64_t lds,
                                    const double *__restrict__ phase, int64_t nrows, int64_t ncols) {
@@ -550,6 +591,9 @@ void ah_destroy(ah_ctx *ctx) {
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
+    if (ctx->blas) cublasDestroy(ctx->blas);
+    for (DevBuf *b : {&ctx->dPtrA, &ctx->dPtrB, &ctx->dPtrC, &ctx->dIdx, &ctx->dBatchA})
+        if (b->p) cudaFree(b->p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -704,6 +748,162 @@ int ah_gather_permuted(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const doubl
     k_gather<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const int64_t *)ctx->dMap1.p, nrows,
                                                           (const int64_t *)ctx->dMap2.p, ncols);
     AH_CUDA(cudaGetLastError());
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return AH_OK;
+}
+
+int ah_symarrow_eigen_batched(ah_ctx *ctx, int64_t nb, int64_t N, const double *D, const double *z, const double *a,
+                              const double *tau, ah_result *out, int64_t ustride) {
+    using namespace ah;
+    if (!ctx) return AH_ERR_INVALID_ARG;
+    if (!D || !z || !a || !out || !out->lambda || nb < 1 || N < 1) return fail(ctx, AH_ERR_INVALID_ARG, "null argument or empty batch");
+    if (out->U && (out->U_mem != AH_MEM_DEVICE || out->ldu < N + 1 || ustride < (N + 1) * out->ldu))
+        return fail(ctx, AH_ERR_INVALID_ARG, "batched solve needs device-resident U blocks (ldu >= N+1, ustride >= (N+1)*ldu)");
+    std::vector<double> maxabs((size_t)nb);
+    for (int64_t b = 0; b < nb; ++b) {
+        const double *Db = D + b * N, *zb = z + b * N;
+        double mz = 0.0;
+        for (int64_t l = 0; l < N; ++l) {
+            if (!std::isfinite(Db[l]) || (l && !(Db[l - 1] > Db[l]))) return fail(ctx, AH_ERR_NOT_ORDERED, "batched: D must be strictly decreasing in every problem");
+            if (zb[l] == 0.0 || !std::isfinite(zb[l])) return fail(ctx, AH_ERR_REDUCIBLE, "batched: zero or non-finite entry in z");
+            mz = std::max(mz, std::fabs(zb[l]));
+        }
+        if (!std::isfinite(a[b])) return fail(ctx, AH_ERR_INVALID_ARG, "batched: non-finite arrow top");
+        maxabs[b] = mz;
+    }
+    ctx->stats = ah_stats{};
+    AH_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t cnt = nb * (N + 1);
+    int rc;
+    if ((rc = ensure(ctx, ctx->dD, nb * N * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dW, nb * N * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dBatchA, 2 * nb * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dOut, out_bytes(cnt)))) return rc;
+    AH_CUDA(cudaMemcpyAsync(ctx->dD.p, D, nb * N * 8, cudaMemcpyHostToDevice, st));
+    AH_CUDA(cudaMemcpyAsync(ctx->dW.p, z, nb * N * 8, cudaMemcpyHostToDevice, st));
+    AH_CUDA(cudaMemcpyAsync(ctx->dBatchA.p, a, nb * 8, cudaMemcpyHostToDevice, st));
+    AH_CUDA(cudaMemcpyAsync((double *)ctx->dBatchA.p + nb, maxabs.data(), nb * 8, cudaMemcpyHostToDevice, st));
+    ctx->stats.h2d_bytes = 2 * nb * N * 8 + 2 * nb * 8;
+    Problem P{};
+    P.N = N; P.D = (const double *)ctx->dD.p; P.w = (const double *)ctx->dW.p;
+    fill_tau(P, tau, N);
+    Outputs O{};
+    {
+        char *p = (char *)ctx->dOut.p;
+        O.lambda = carve<double>(p, cnt); O.sind = carve<int64_t>(p, cnt);
+        O.kb = carve<double>(p, cnt); O.kz = carve<double>(p, cnt); O.knu = carve<double>(p, cnt); O.krho = carve<double>(p, cnt);
+        O.qout = carve<int64_t>(p, cnt); O.steps = carve<int32_t>(p, cnt); O.status = carve<int32_t>(p, cnt);
+    }
+    O.U = out->U; O.ldu = out->ldu;
+    AH_CUDA(cudaEventRecord(ctx->ev[0], st));
+    const int grid = (int)std::min<int64_t>(cnt, (int64_t)ctx->sm_count * 32);
+    const double *av = (const double *)ctx->dBatchA.p, *mx = av + nb;
+    if (N <= 64) k_full_batched<KIND_ARROW, 32><<<grid, 32, 0, st>>>(P, O, nb, av, mx, ustride);
+    else if (N <= 512) k_full_batched<KIND_ARROW, 128><<<grid, 128, 0, st>>>(P, O, nb, av, mx, ustride);
+    else k_full_batched<KIND_ARROW, 256><<<grid, 256, 0, st>>>(P, O, nb, av, mx, ustride);
+    AH_CUDA(cudaGetLastError());
+    AH_CUDA(cudaEventRecord(ctx->ev[1], st));
+    if ((rc = ensure_pinned(ctx, out_bytes(cnt)))) return rc;
+    AH_CUDA(cudaMemcpyAsync(ctx->hPinned, ctx->dOut.p, out_bytes(cnt), cudaMemcpyDeviceToHost, st));
+    AH_CUDA(cudaStreamSynchronize(st));
+    {
+        char *p = (char *)ctx->hPinned;
+        double *lam = carve<double>(p, cnt);
+        int64_t *sind = carve<int64_t>(p, cnt);
+        double *kb = carve<double>(p, cnt), *kz = carve<double>(p, cnt), *knu = carve<double>(p, cnt), *krho = carve<double>(p, cnt);
+        int64_t *qout = carve<int64_t>(p, cnt);
+        int32_t *steps = carve<int32_t>(p, cnt), *status = carve<int32_t>(p, cnt);
+        std::memcpy(out->lambda, lam, cnt * 8);
+        if (out->sind) std::memcpy(out->sind, sind, cnt * 8);
+        if (out->kb) std::memcpy(out->kb, kb, cnt * 8);
+        if (out->kz) std::memcpy(out->kz, kz, cnt * 8);
+        if (out->knu) std::memcpy(out->knu, knu, cnt * 8);
+        if (out->krho) std::memcpy(out->krho, krho, cnt * 8);
+        if (out->qout) std::memcpy(out->qout, qout, cnt * 8);
+        if (out->steps) std::memcpy(out->steps, steps, cnt * 4);
+        if (out->status) std::memcpy(out->status, status, cnt * 4);
+    }
+    float ms = 0.f;
+    AH_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->stats.kernel_ms = ms; ctx->stats.full_ms = ms; ctx->stats.launches = 1; ctx->stats.n_full = cnt;
+    ctx->stats.d2h_bytes = cnt * (8 * 7 + 4 * 2);
+    return AH_OK;
+}
+
+int ah_gather_elements(ah_ctx *ctx, const double *src_dev, const int64_t *idx, int64_t count, double *out) {
+    if (!ctx || !src_dev || !idx || !out || count < 1) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->dIdx, count * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dScale, count * 8))) return rc;
+    AH_CUDA(cudaMemcpyAsync(ctx->dIdx.p, idx, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_gather_elems<<<(int)std::min<int64_t>((count + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+        (double *)ctx->dScale.p, src_dev, (const int64_t *)ctx->dIdx.p, count);
+    AH_CUDA(cudaGetLastError());
+    AH_CUDA(cudaMemcpyAsync(out, ctx->dScale.p, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return AH_OK;
+}
+
+int ah_gather_permuted_batched(ah_ctx *ctx, int64_t nb, double *dst_dev, int64_t dst_stride, int64_t ld_dst,
+                               const double *src_dev, int64_t src_stride, int64_t ld_src, const int64_t *rows,
+                               int64_t nrows, const int64_t *cols, int64_t ncols) {
+    if (!ctx || !dst_dev || !src_dev || !rows || !cols || nb < 1 || nrows < 1 || ncols < 1 || ld_dst < nrows) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->dMap1, nb * nrows * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dMap2, nb * ncols * 8))) return rc;
+    AH_CUDA(cudaMemcpyAsync(ctx->dMap1.p, rows, nb * nrows * 8, cudaMemcpyHostToDevice, ctx->stream));
+    AH_CUDA(cudaMemcpyAsync(ctx->dMap2.p, cols, nb * ncols * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_gather_batched<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(dst_dev, dst_stride, ld_dst, src_dev, src_stride, ld_src,
+                                                                  (const int64_t *)ctx->dMap1.p, nrows, (const int64_t *)ctx->dMap2.p, ncols, nb);
+    AH_CUDA(cudaGetLastError());
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return AH_OK;
+}
+
+int ah_copy2d_batched(ah_ctx *ctx, int64_t nb, int64_t nrows, int64_t ncols, const uint64_t *dst_ptrs, int64_t ld_dst,
+                      const uint64_t *src_ptrs, int64_t ld_src) {
+    if (!ctx || !dst_ptrs || !src_ptrs || nb < 1 || nrows < 1 || ncols < 1) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->dPtrA, nb * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dPtrC, nb * 8))) return rc;
+    AH_CUDA(cudaMemcpyAsync(ctx->dPtrA.p, src_ptrs, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    AH_CUDA(cudaMemcpyAsync(ctx->dPtrC.p, dst_ptrs, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_copy2d_batched<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const uint64_t *)ctx->dPtrC.p, ld_dst, (const uint64_t *)ctx->dPtrA.p, ld_src,
+                                                                  nrows, ncols, nb);
+    AH_CUDA(cudaGetLastError());
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return AH_OK;
+}
+
+int ah_dgemm_batched(ah_ctx *ctx, int64_t nb, int64_t m, int64_t n, int64_t k, const uint64_t *A_ptrs, int64_t lda,
+                     const uint64_t *B_ptrs, int64_t ldb, const uint64_t *C_ptrs, int64_t ldc) {
+    if (!ctx || !A_ptrs || !B_ptrs || !C_ptrs || nb < 1 || m < 1 || n < 1 || k < 1 || lda < m || ldb < k || ldc < m) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->blas) {
+        if (cublasCreate(&ctx->blas) != CUBLAS_STATUS_SUCCESS) { ctx->blas = nullptr; return fail(ctx, AH_ERR_CUDA_BASE, "cublasCreate failed"); }
+    }
+    if (cublasSetStream(ctx->blas, ctx->stream) != CUBLAS_STATUS_SUCCESS) return fail(ctx, AH_ERR_CUDA_BASE, "cublasSetStream failed");
+    int rc;
+    if ((rc = ensure(ctx, ctx->dPtrA, nb * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dPtrB, nb * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dPtrC, nb * 8))) return rc;
+    AH_CUDA(cudaMemcpyAsync(ctx->dPtrA.p, A_ptrs, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    AH_CUDA(cudaMemcpyAsync(ctx->dPtrB.p, B_ptrs, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    AH_CUDA(cudaMemcpyAsync(ctx->dPtrC.p, C_ptrs, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const double one = 1.0, zero = 0.0;
+    cublasStatus_t cs;
+    if (nb == 1) {
+        cs = cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, (int)n, (int)k, &one, (const double *)A_ptrs[0], (int)lda,
+                         (const double *)B_ptrs[0], (int)ldb, &zero, (double *)C_ptrs[0], (int)ldc);
+    } else {
+        cs = cublasDgemmBatched(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, (int)n, (int)k, &one, (const double *const *)ctx->dPtrA.p, (int)lda,
+                                (const double *const *)ctx->dPtrB.p, (int)ldb, &zero, (double *const *)ctx->dPtrC.p, (int)ldc, (int)nb);
+    }
+    if (cs != CUBLAS_STATUS_SUCCESS) return fail(ctx, AH_ERR_CUDA_BASE, "cublasDgemm(Batched) failed with status " + std::to_string((int)cs));
     AH_CUDA(cudaStreamSynchronize(ctx->stream));
     return AH_OK;
 }

@@ -360,9 +360,9 @@ def svd(A, tau=None, **kw):
     raise TypeError(f"svd: unsupported type {type(A).__name__}")
 
 
-def tdc(dv, ev, *, ctx: Context | None = None, rotation="reference"):
-    """tdc(T::SymTridiagonal) (arrowhead7.jl:10-36): recursive divide and conquer; the arrow merges run on
-    the GPU, the back-transform GEMMs on the host for now ("next")."""
+def tdc_recursive(dv, ev, *, ctx: Context | None = None, rotation="reference"):
+    """tdc(T::SymTridiagonal) (arrowhead7.jl:10-36) exactly as written: recursion, one arrow merge per call on the
+    GPU, the back-transform products on the host.  Kept for small matrices and as the cross-check of tdc_device."""
     dv = np.asarray(dv, np.float64)
     ev = np.asarray(ev, np.float64)
     n = dv.size
@@ -372,8 +372,8 @@ def tdc(dv, ev, *, ctx: Context | None = None, rotation="reference"):
         E, _ = eigen_symarrow(SymArrow([dv[0]], [ev[0]], dv[1], 2), ctx=ctx, rotation=rotation)
         return E
     k = n // 2
-    E1 = tdc(dv[:k], ev[: k - 1], ctx=ctx, rotation=rotation)
-    E2 = tdc(dv[k + 1:], ev[k + 1:], ctx=ctx, rotation=rotation)
+    E1 = tdc_recursive(dv[:k], ev[: k - 1], ctx=ctx, rotation=rotation)
+    E2 = tdc_recursive(dv[k + 1:], ev[k + 1:], ctx=ctx, rotation=rotation)
     Dm = np.concatenate([E1.values, E2.values])
     zm = np.concatenate([E1.vectors[-1, :] * ev[k - 1], E2.vectors[0, :] * ev[k]])
     E, _ = eigen_symarrow(SymArrow(Dm, zm, dv[k], k + 1), ctx=ctx, rotation=rotation)
@@ -381,3 +381,166 @@ def tdc(dv, ev, *, ctx: Context | None = None, rotation="reference"):
     W[:k, :] = E1.vectors @ W[:k, :]
     W[k + 1:, :] = E2.vectors @ W[k + 1:, :]
     return Eigen(E.values, W)
+
+
+_TDC_BIG = 2048      # merges with at least this many poles go through the fast pipeline one by one
+
+
+def tdc_device(dv, ev, *, ctx: Context | None = None, vectors="host", rotation="reference"):
+    """tdc(T::SymTridiagonal) (arrowhead7.jl:10-36) with everything of size n^2 resident on the GPU.
+
+    The recursion tree (k = div(n,2); T1 = T[1:k], T2 = T[k+2:n], arrowhead7.jl:21-23) is walked bottom-up, one
+    height at a time: all merges of one height are independent, so their arrow problems are solved in ONE batched
+    launch (ah_symarrow_eigen_batched; large ones through the fast pipeline), their merge vectors z (:28) are read
+    from the resident eigenvector blocks, the final `view(U,rows,es)` of the arrow driver is one batched gather, and
+    the back-transforms `E1.vectors*E.vectors[1:k,:]`, `E2.vectors*E.vectors[k+2:n,:]` (:32-33) are two
+    cublasDgemmBatched calls per size class.  Host work is the reference's host logic only: stable sorts, the
+    (exact) deflation tests, index bookkeeping.  Node [lo,hi) keeps its eigenvectors in the diagonal block
+    [lo:hi, lo:hi] of one of three n x n buffers (height mod 3), so children are never overwritten while read.
+    Merges that need deflation take the general per-problem driver (eigen_symarrow)."""
+    ctx = ctx or get_context()
+    dv = np.ascontiguousarray(dv, np.float64)
+    ev = np.ascontiguousarray(ev, np.float64)
+    n = dv.size
+    if n <= 2:
+        return tdc_recursive(dv, ev, ctx=ctx, rotation=rotation)
+    height = lambda m: int(m).bit_length() - 1                        # floor(log2(m)); 0 for a leaf
+    by_height: dict[int, list] = {}
+    stack = [(0, n)]
+    while stack:
+        lo, hi = stack.pop()
+        m = hi - lo
+        if m < 2:
+            continue
+        by_height.setdefault(height(m), []).append((lo, hi))
+        k = m // 2
+        stack.append((lo, lo + k))
+        stack.append((lo + k + 1, hi))
+    # one resident workspace per context, reused across calls (cudaMalloc/cudaFree of GBs cost more than the solve):
+    # three n x n eigenvector buffers side by side, then the solver-output and permuted-output scratch (n^2 each)
+    ws = getattr(ctx, "_tdc_workspace", None)
+    if ws is None or ws.nrows != n:
+        if ws is not None:
+            ws.free()
+        ws = ctx._tdc_workspace = DeviceMatrix(ctx, n, 5 * n)
+    Q = ws
+    qbase = lambda t: Q.ptr + 8 * t * n * n
+    s_base, wp_base = qbase(3), qbase(4)
+
+    class _View:                                                      # a slice of the workspace with DeviceMatrix's face
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def free(self):
+            pass
+    ctx.set_identity(Q.ptr, n, n, n)                                  # leaves: U = [1] in buffer 0
+    lam = {(i, i + 1): dv[i:i + 1] for i in range(n)}                 # eigenvalues of every finished node
+    stats = {"levels": 0, "batched_problems": 0, "pipeline_problems": 0, "driver_problems": 0, "gemm_calls": 0}
+    for h in sorted(by_height):
+        stats["levels"] += 1
+        groups: dict[int, list] = {}
+        for node in by_height[h]:
+            groups.setdefault(node[1] - node[0], []).append(node)
+        for m, nodes in sorted(groups.items()):
+            nodes.sort()
+            nb, k = len(nodes), m // 2
+            r, N = m - k - 1, m - 1
+            los = np.array([lo for lo, _ in nodes], np.int64)
+            p = los + k                                               # pivot rows
+            tl, tr, tq = height(k) % 3, (height(r) % 3 if r else 0), h % 3
+            # ---- merge problems: D = [L1; L2], z = [U1[end,:]*ev[p-1]; U2[1,:]*ev[p]], a = dv[p], arrow top at k+1
+            D = np.empty((nb, N)); z = np.empty((nb, N))
+            cl = los[:, None] + np.arange(k)[None, :]
+            idx = [((tl * n + cl) * n + (p - 1)[:, None]).ravel()]
+            if r:
+                cr = (p + 1)[:, None] + np.arange(r)[None, :]
+                idx.append(((tr * n + cr) * n + (p + 1)[:, None]).ravel())
+            g = ctx.gather_elements(Q.ptr, np.concatenate(idx))
+            z[:, :k] = g[: nb * k].reshape(nb, k) * ev[p - 1][:, None]
+            if r:
+                z[:, k:] = g[nb * k:].reshape(nb, r) * ev[p][:, None]
+            for b, (lo, hi) in enumerate(nodes):
+                D[b, :k] = lam.pop((lo, lo + k))
+                if r:
+                    D[b, k:] = lam.pop((lo + k + 1, hi))
+            a = dv[p]
+            # ---- the arrow driver's host logic (arrowhead3.jl:571-573, 583-623), vectorised over the group
+            is_ = np.argsort(-D, axis=1, kind="stable")
+            Ds = np.take_along_axis(D, is_, axis=1); zs = np.take_along_axis(z, is_, axis=1)
+            needs_driver = (zs == 0).any(axis=1) | (Ds == 0).any(axis=1)
+            if N > 1:
+                needs_driver |= (Ds[:, :-1] == Ds[:, 1:]).any(axis=1)
+            fast = np.flatnonzero(~needs_driver)
+            S = _View(s_base)                                         # solver output, one m x m block per node (nb*m*m <= n*n)
+            Wp = _View(wp_base)                                       # after the driver's row/column permutation
+            L = np.empty((nb, m))
+            if fast.size:
+                if N >= _TDC_BIG:
+                    for b in fast:
+                        res = ctx.symarrow(Ds[b], zs[b], a[b], vectors=False, U_dev=S.ptr + 8 * b * m * m, ldu=m)
+                        L[b] = res.lam
+                    stats["pipeline_problems"] += int(fast.size)
+                else:
+                    # contiguous sub-batch of the solvable nodes
+                    Sf = S if fast.size == nb else DeviceMatrix(ctx, m * m, fast.size)
+                    res = ctx.symarrow_batched(Ds[fast], zs[fast], a[fast], U_dev=Sf.ptr, ldu=m, ustride=m * m)
+                    L[fast] = res.lam.reshape(fast.size, m)
+                    if Sf is not S:
+                        ctx.copy2d_batched(m * m, 1, S.ptr + 8 * m * m * fast.astype(np.uint64), m * m,
+                                           Sf.ptr + 8 * m * m * np.arange(fast.size, dtype=np.uint64), m * m)
+                        Sf.free()
+                    stats["batched_problems"] += int(fast.size)
+                es = np.argsort(-L[fast], axis=1, kind="stable")
+                isi = np.argsort(is_[fast], axis=1, kind="stable")
+                rows = np.concatenate([isi[:, :k], np.full((fast.size, 1), N, np.int64), isi[:, k:]], axis=1)
+                if fast.size == nb:
+                    ctx.gather_permuted_batched(Wp.ptr, m * m, m, S.ptr, m * m, m, rows, es)
+                else:
+                    for j, b in enumerate(fast):
+                        ctx.gather_permuted_batched(Wp.ptr + 8 * b * m * m, m * m, m, S.ptr + 8 * b * m * m, m * m, m,
+                                                    rows[j:j + 1], es[j:j + 1])
+                L[fast] = np.take_along_axis(L[fast], es, axis=1)
+            for b in np.flatnonzero(needs_driver):                    # deflation: the general driver, one problem at a time
+                E, _ = eigen_symarrow(SymArrow(D[b], z[b], a[b], k + 1), ctx=ctx, vectors="device", rotation=rotation)
+                L[b] = E.values
+                ctx.copy2d_batched(m, m, [Wp.ptr + 8 * b * m * m], m, [E.vectors.ptr], E.vectors.ld)
+                E.vectors.free()
+                stats["driver_problems"] += 1
+            S.free()
+            # ---- back-transform into buffer h mod 3 (arrowhead7.jl:32-33) + the pivot row
+            wp = Wp.ptr + 8 * m * m * np.arange(nb, dtype=np.uint64)
+            qout = np.uint64(qbase(tq)) + 8 * (los * n + los).astype(np.uint64)
+            ql = np.uint64(qbase(tl)) + 8 * (los * n + los).astype(np.uint64)
+            ctx.dgemm_batched(k, m, k, ql, n, wp, m, qout, n)
+            ctx.copy2d_batched(1, m, qout + np.uint64(8 * k), n, wp + np.uint64(8 * k), m)
+            stats["gemm_calls"] += 1
+            if r:
+                qr = np.uint64(qbase(tr)) + 8 * ((p + 1) * n + (p + 1)).astype(np.uint64)
+                ctx.dgemm_batched(r, m, r, qr, n, wp + np.uint64(8 * (k + 1)), m, qout + np.uint64(8 * (k + 1)), n)
+                stats["gemm_calls"] += 1
+            Wp.free()
+            for b, node in enumerate(nodes):
+                lam[node] = L[b]
+    values = lam[(0, n)]
+    troot = height(n) % 3
+    E = Eigen(values, None)
+    E.stats = stats
+    if vectors is None:
+        return E
+    out = DeviceMatrix(ctx, n, n)
+    ctx.copy2d_batched(n, n, [out.ptr], n, [qbase(troot)], n)
+    if vectors == "device":
+        E.vectors = out
+    else:
+        E.vectors = out.to_host()
+        out.free()
+    return E
+
+
+def tdc(dv, ev, *, ctx: Context | None = None, rotation="reference", method="auto", vectors="host"):
+    """tdc(T::SymTridiagonal) (arrowhead7.jl:10-36).  method: "recursive" (host back-transform, the literal
+    recursion), "device" (level-batched, resident), "auto" (device from n = 64 on)."""
+    n = np.asarray(dv).size
+    if method == "recursive" or (method == "auto" and n < 64):
+        return tdc_recursive(dv, ev, ctx=ctx, rotation=rotation)
+    return tdc_device(dv, ev, ctx=ctx, vectors=vectors, rotation=rotation)

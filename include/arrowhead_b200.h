@@ -144,6 +144,32 @@ int ah_apply_givens_rows(ah_ctx *ctx, double *U_dev, int64_t ld, int64_t ncols, 
 int ah_gather_permuted(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src,
                        const int64_t *rows, int64_t nrows, const int64_t *cols, int64_t ncols);
 
+/* ---- batched primitives for tdc() (src/arrowhead7.jl:10-36): one divide-and-conquer level = many independent
+ * arrow merges of (nearly) equal size, then two back-transform GEMMs per merge ---------------------------------- */
+/* nb ordered irreducible SymArrow problems with the same number of poles N, solved in ONE launch by the complete
+ * per-k solver (every branch of arrowhead3.jl:419-550).  D, z: host [nb*N] (problem b at offset b*N), a: host [nb].
+ * out->lambda/sind/...: host arrays of nb*(N+1) entries (problem b at offset b*(N+1)).  out->U: NULL or a DEVICE
+ * pointer; problem b's (N+1)x(N+1) eigenvector matrix goes to U + b*ustride with leading dimension out->ldu. */
+int ah_symarrow_eigen_batched(ah_ctx *ctx, int64_t nb, int64_t N, const double *D, const double *z, const double *a,
+                              const double *tau, ah_result *out, int64_t ustride);
+/* out[t] = src_dev[idx[t]] (element offsets, host index vector, host result): the merge vectors
+ * z = [U1[end,:]; U2[1,:]] of arrowhead7.jl:28 are read straight out of the resident eigenvector blocks. */
+int ah_gather_elements(ah_ctx *ctx, const double *src_dev, const int64_t *idx, int64_t count, double *out);
+/* nb gathers of equal shape: dst_b[r,c] = src_b[rows[b*nrows+r], cols[b*ncols+c]], dst_b = dst + b*dst_stride,
+ * src_b = src + b*src_stride (all device, column-major); rows/cols are host index vectors. */
+int ah_gather_permuted_batched(ah_ctx *ctx, int64_t nb, double *dst_dev, int64_t dst_stride, int64_t ld_dst,
+                               const double *src_dev, int64_t src_stride, int64_t ld_src, const int64_t *rows,
+                               int64_t nrows, const int64_t *cols, int64_t ncols);
+/* nb strided 2-D copies of equal shape between device matrices given by their (device) addresses:
+ * dst_ptrs[b][c*ld_dst + r] = src_ptrs[b][c*ld_src + r]. */
+int ah_copy2d_batched(ah_ctx *ctx, int64_t nb, int64_t nrows, int64_t ncols, const uint64_t *dst_ptrs, int64_t ld_dst,
+                      const uint64_t *src_ptrs, int64_t ld_src);
+/* C_b = A_b * B_b (m x k times k x n), all device, column-major, addresses in host arrays: the back-transform
+ * `E.vectors[1:k,:] = E1.vectors*E.vectors[1:k,:]` (arrowhead7.jl:32-33) of a whole level in one cuBLAS
+ * cublasDgemmBatched call (a plain library GEMM; the one tensor-core-eligible operation of the package). */
+int ah_dgemm_batched(ah_ctx *ctx, int64_t nb, int64_t m, int64_t n, int64_t k, const uint64_t *A_ptrs, int64_t lda,
+                     const uint64_t *B_ptrs, int64_t ldb, const uint64_t *C_ptrs, int64_t ldc);
+
 /* Hermitian wrappers (src/hermitian.jl:107-115, 131-139: `Diagonal(c)*U.vectors`):
  * dst[(c*ld_dst + r)*ncomp + q] = phase[r*ncomp + q] * src[c*ld_src + r], q < ncomp (2: complex, 4: quaternion).
  * src is the real eigenvector matrix on the device, dst a device buffer of nrows*ncols*ncomp doubles

@@ -458,7 +458,8 @@ def test_config5_tdc_n8192(gpu_ctx):
     n = 8192
     rng = np.random.default_rng(421)
     dv, ev = 2.0 + 1e-3 * rng.standard_normal(n), -1.0 + 1e-3 * rng.standard_normal(n - 1)
-    E = ab.tdc(dv, ev, ctx=gpu_ctx)
+    E = ab.tdc(dv, ev, ctx=gpu_ctx)                                      # level-batched, device-resident (tdc_device)
+    assert E.stats["batched_problems"] > 4000 and E.stats["pipeline_problems"] >= 3
     ref = eigh_tridiagonal(dv, ev, eigvals_only=True)[::-1]
     scale = np.abs(ref).max()
     assert np.max(np.abs(np.sort(E.values)[::-1] - ref)) <= 50 * n * EPS * scale
@@ -469,3 +470,39 @@ def test_config5_tdc_n8192(gpu_ctx):
     Tb[1:] += ev[:, None] * blk[:-1]
     Tb[:-1] += ev[:, None] * blk[1:]
     assert np.linalg.norm(Tb - blk * E.values[1000:1256]) <= 50 * n * EPS * scale
+
+
+@pytest.mark.parametrize("n", [3, 4, 7, 21, 100, 257])
+def test_tdc_device_matches_the_literal_recursion(gpu_ctx, n):
+    """tdc_device (batched levels, cuBLAS back-transform) vs tdc_recursive (arrowhead7.jl:10-36 as written)."""
+    rng = np.random.default_rng(n)
+    dv, ev = 2.0 + 0.1 * rng.standard_normal(n), -1.0 + 0.1 * rng.standard_normal(n - 1)
+    R = ab.tdc_recursive(dv, ev, ctx=gpu_ctx)
+    Dv = ab.tdc_device(dv, ev, ctx=gpu_ctx)
+    scale = np.abs(R.values).max()
+    assert np.max(np.abs(Dv.values - R.values)) <= 8 * n * EPS * scale
+    assert np.max(np.abs(np.abs(Dv.vectors) - np.abs(R.vectors))) <= 1e4 * n * EPS
+    T = np.diag(dv) + np.diag(ev, 1) + np.diag(ev, -1)
+    assert np.linalg.norm(T @ Dv.vectors - Dv.vectors * Dv.values) <= 20 * n * EPS * scale
+    assert np.linalg.norm(Dv.vectors.T @ Dv.vectors - np.eye(n)) <= 20 * n * EPS
+
+
+def test_tdc_device_wilkinson_w21_and_duplicate_deflation(gpu_ctx, golden):
+    """W21 through the device path (runtests.jl:91-115; the literal 5 eps bar is applied to the recursion in
+    test_tdc_w21_gpu) and a matrix whose halves have identical spectra (exact-duplicate deflation in every merge)."""
+    c = golden["tdc_w21"]
+    E = ab.tdc_device(c["dv"], c["ev"], ctx=gpu_ctx)
+    assert np.linalg.norm(np.sort(E.values) - np.sort(c["values"])) < 40 * EPS
+    n = 31
+    dv, ev = np.full(n, 2.0), np.full(n - 1, -1.0)                      # T1 and T2 of every split are identical
+    exact = 2.0 - 2.0 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
+    T = np.diag(dv) + np.diag(ev, 1) + np.diag(ev, -1)
+    # the reference applies the deflation rotations as R where the algebra needs R' (arrowhead3.jl:634-635), so its
+    # eigenvectors are wrong whenever D-deflation fires: "reference" must reproduce that, "transpose" must be right
+    E = ab.tdc_device(dv, ev, ctx=gpu_ctx, rotation="transpose")
+    assert np.max(np.abs(np.sort(E.values) - np.sort(exact))) <= 50 * EPS
+    assert E.stats["driver_problems"] > 0
+    assert np.linalg.norm(T @ E.vectors - E.vectors * E.values) <= 200 * EPS
+    Eref = ab.tdc_device(dv, ev, ctx=gpu_ctx)
+    Rref = ab.tdc_recursive(dv, ev, ctx=gpu_ctx)
+    assert np.max(np.abs(np.sort(Eref.values) - np.sort(Rref.values))) <= 50 * EPS
