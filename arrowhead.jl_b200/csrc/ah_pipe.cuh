@@ -292,9 +292,13 @@ constexpr int BW = BT / 32;      // warps
 constexpr int BJ = 8;            // eigenpair slots per CTA
 constexpr int BE = 4;            // poles per thread per tile
 constexpr int BTL = BT * BE;     // poles per tile (2048)
-constexpr int BS = 4;            // ring stages
+#ifndef AH_BS
+#define AH_BS 4
+#endif
+constexpr int BS = AH_BS;        // ring stages
 constexpr int TILE_POLES = 2048; // inputs are padded to a multiple of this (a multiple of BTL)
 static_assert(TILE_POLES % BTL == 0, "tile size");
+static_assert((BS & (BS - 1)) == 0, "ring depth must be a power of two (stage = g & (BS-1); measured: BS = 3, 5, 6 cost 7 % in index arithmetic, BS = 2 and 4 perform alike)");
 
 enum : int { PH_FREE = 0, PH_BISECT, PH_DONE };
 
@@ -427,18 +431,21 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
     if (ROUND == 1) cnt = (int64_t)dcount[2];   // round 1 works through the Remedy-3 list
     __syncthreads();
 
-    long long g_issue = 0;   // tiles issued (thread 0 only)
-    long long g = 0;         // tiles consumed
-    auto issue_tile = [&](long long gi) {
-        const int s = (int)(gi % BS);
-        const long long use = gi / BS;
-        if (use > 0) mbar_wait(&sh.empty[s], (uint32_t)((use - 1) & 1));
-        const int tile = (int)(gi % ntiles);
+    bool wrapped = false;    // g_issue has wrapped around 2^32 at least once
+    uint32_t g_issue = 0;    // tiles issued (thread 0 only); wraps mod 2^32, a multiple of 2*BS -> parities stay consistent
+    uint32_t g = 0;          // tiles consumed
+    uint32_t issue_pos = 0;  // g_issue mod ntiles
+    auto issue_tile = [&](uint32_t gi) {
+        const int s = (int)(gi & (BS - 1));
+        const uint32_t use = gi / BS;
+        if (gi >= (uint32_t)BS || wrapped) mbar_wait(&sh.empty[s], (use - 1u) & 1u);
+        const int tile = (int)issue_pos;
+        issue_pos = (issue_pos + 1 == (uint32_t)ntiles) ? 0u : issue_pos + 1;
         mbar_arrive_expect_tx(&sh.full[s], 2u * BTL * 8u);
         bulk_g2s(&sh.tileD[s][0], P.D + (int64_t)tile * BTL, BTL * 8u, &sh.full[s]);
         bulk_g2s(&sh.tileW[s][0], P.w2 + (int64_t)tile * BTL, BTL * 8u, &sh.full[s]);
     };
-    if (tid == 0) { for (; g_issue < BS - 1; ++g_issue) issue_tile(g_issue); }
+    if (tid == 0) { for (; g_issue < (uint32_t)(BS - 1); ++g_issue) issue_tile(g_issue); }
 
     bool first = true;
     while (true) {
@@ -544,9 +551,9 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
 
         // ================= the sweep =================
         for (int tile = 0; tile < ntiles; ++tile, ++g) {
-            if (tid == 0) { issue_tile(g_issue); ++g_issue; }
-            const int s = (int)(g % BS);
-            mbar_wait(&sh.full[s], (uint32_t)((g / BS) & 1));
+            if (tid == 0) { issue_tile(g_issue); if (++g_issue == 0u) wrapped = true; }
+            const int s = (int)(g & (BS - 1));
+            mbar_wait(&sh.full[s], (g / BS) & 1u);
             double Dv[BE], W2[BE];
 #pragma unroll
             for (int e = 0; e < BE; e += 2) {
@@ -614,7 +621,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
 
     // drain the prefetched tiles before the CTA (and its shared memory) goes away
     if (tid == 0) {
-        for (long long gi = g; gi < g_issue; ++gi) mbar_wait(&sh.full[(int)(gi % BS)], (uint32_t)((gi / BS) & 1));
+        for (uint32_t gi = g; gi != g_issue; ++gi) mbar_wait(&sh.full[(int)(gi & (BS - 1))], (gi / BS) & 1u);
     }
 }
 

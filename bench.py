@@ -282,6 +282,22 @@ def run_ours(args):
         assert np.array_equal(r2.lam, res.lam)
         assert torch.equal(Uh[cnt // 2].to(dev), U[cnt // 2])
 
+    allgather_ms = None
+    if dist is not None and args.allgather:
+        # optional, outside the headline: every rank ends up with all of U (NCCL all_gather of the column blocks)
+        from arrowhead_b200.sharding import allgather_columns
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        Ufull = allgather_columns(U, n, n, world, rank, dist)
+        a1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        allgather_ms = float(tt[0])
+        assert Ufull.shape == (n, n) and torch.equal(Ufull[k0 - 1:k1], U)
+        del Ufull
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = host_threads()
@@ -299,6 +315,7 @@ def run_ours(args):
             "config": {"workload": f"SymArrow n={n} full eigen(), GenSymArrow-like rng(421), ordered, arrow top last",
                        "parallelism": f"k-range x{world}", "U": "device-resident, column blocks per rank",
                        "l2": "256 MB flush write before every step; the step itself streams out n^2*8 bytes >> L2",
+                       "allgather_U_ms": allgather_ms,
                        "kernel_ms_per_step_rank0": kern_ms / args.steps,
                        "kernel_ms_breakdown_rank0": {k: res.stats[k] for k in ("prep_ms", "bisect_ms", "vec_ms", "full_ms")},
                        "n_full_rank0": int(res.stats["n_full"]), "n_rem3_rank0": int(res.stats["n_rem3"]),
@@ -353,6 +370,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="symarrow", choices=["symarrow", "tdc"])
+    ap.add_argument("--allgather", action="store_true", help="N>1: also time an NCCL all-gather of U (reported separately)")
     args = ap.parse_args()
     if args.workload == "tdc":
         run_tdc(args)

@@ -28,6 +28,14 @@ def _worker(rank, world, port, nk, q):
     k0, k1 = ab.k_partition(nk, world, rank)
     local = np.array([float(k) ** 2 for k in range(k0, k1 + 1)])
     full = gather_values(local, nk, world, rank, dist)
+    # column blocks of U (row c of the [cnt, nrows] tensor = eigenvector column k0+c), ragged split
+    import torch
+    from arrowhead_b200.sharding import allgather_columns
+    nrows = 5
+    Uloc = torch.tensor([[100.0 * k + r for r in range(nrows)] for k in range(k0, k1 + 1)], dtype=torch.float64)
+    Ufull = allgather_columns(Uloc, nrows, nk, world, rank, dist)
+    assert Ufull.shape == (nk, nrows)
+    assert torch.equal(Ufull, torch.tensor([[100.0 * k + r for r in range(nrows)] for k in range(1, nk + 1)], dtype=torch.float64))
     q.put((rank, k0, k1, full.tolist()))
     dist.barrier()
     dist.destroy_process_group()
