@@ -37,6 +37,9 @@ struct ah_ctx {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // high priority: the short Remedy-3 round runs beside k_vec
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    std::vector<cudaEvent_t> side_ev;     // 2 timing events per column block on the side stream
     cudaStream_t stream = nullptr;  // the stream kernels run on (own_stream or caller's)
     cudaEvent_t ev[12] = {};
     cudaEvent_t ev_stage[2] = {};
@@ -274,6 +277,11 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         AH_CUDA(cudaEventCreate(&e));
         ctx->chunk_ev.push_back(e);
     }
+    while ((int)ctx->side_ev.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        AH_CUDA(cudaEventCreate(&e));
+        ctx->side_ev.push_back(e);
+    }
     for (int64_t c0 = 0; c0 < cnt; c0 += chunk, ++nbuf) {
         const int64_t cc = std::min(chunk, cnt - c0);
         const int slot = nbuf & 1;
@@ -306,22 +314,36 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             AH_CUDA(cudaEventRecord(E[1], st));
             rc = ah::launch_bisect(L.kind, 0, P, Oc, ks, kb, cc, dlist, rlist, dcount, ctx->sm_count, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect launch");
-            // Remedy 3 on the fast path: re-shift (k_rem3_prep) and bisect again (round 1).  The list length
-            // lives on the device; the grids are sized for the ~1-3 % of eigenpairs that usually need it.
+            AH_CUDA(cudaEventRecord(E[2], st));
+            // Remedy 3 on the fast path: re-shift (k_rem3_prep) and bisect again (round 1) for the ~1 % of eigenpairs
+            // on the list (its length lives on the device).  The round is short and latency-bound, so it runs on a
+            // high-priority side stream BESIDE the eigenvector kernel of everything round 0 finished; the listed
+            // eigenpairs get their vectors in a second, list-driven k_vec after the join.
             {
                 const int64_t guess = std::max<int64_t>(1, std::min<int64_t>(cc, (int64_t)ctx->sm_count * 2 * ah::BJ));   // full grid; idle slots are skipped
-                rc = ah::launch_rem3_prep(L.kind, P, ks, kb, guess, rlist, dlist, dcount, ctx->sm_count, st);
+                const bool overlap = wantU || wantV;
+                cudaStream_t rs = overlap ? ctx->side_stream : st;
+                cudaEvent_t *SE = &ctx->side_ev[2 * (size_t)nbuf];
+                if (overlap) {
+                    AH_CUDA(cudaEventRecord(ctx->ev_fork, st));
+                    AH_CUDA(cudaStreamWaitEvent(rs, ctx->ev_fork, 0));
+                }
+                AH_CUDA(cudaEventRecord(SE[0], rs));
+                rc = ah::launch_rem3_prep(L.kind, P, ks, kb, guess, rlist, dlist, dcount, ctx->sm_count, rs);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_rem3_prep launch");
-                rc = ah::launch_bisect(L.kind, 1, P, Oc, ks, kb, guess, dlist, rlist, dcount, ctx->sm_count, st);
+                rc = ah::launch_bisect(L.kind, 1, P, Oc, ks, kb, guess, dlist, rlist, dcount, ctx->sm_count, rs);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect round 1 launch");
+                AH_CUDA(cudaEventRecord(SE[1], rs));
                 ctx->stats.launches += 2;
-            }
-            AH_CUDA(cudaEventRecord(E[2], st));
-            ctx->stats.launches += 2;
-            if (wantU || wantV) {
-                rc = ah::launch_vec(L.kind, P, Oc, ks, kb, cc, st);
-                if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_vec launch");
-                ctx->stats.launches += 1;
+                if (overlap) {
+                    AH_CUDA(cudaEventRecord(ctx->ev_join, rs));
+                    rc = ah::launch_vec(L.kind, P, Oc, ks, kb, cc, nullptr, nullptr, ctx->sm_count, st);
+                    if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_vec launch");
+                    AH_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+                    rc = ah::launch_vec(L.kind, P, Oc, ks, kb, guess, rlist, dcount + 2, ctx->sm_count, st);
+                    if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_vec (Remedy-3 list) launch");
+                    ctx->stats.launches += 2;
+                }
             }
             AH_CUDA(cudaEventRecord(E[3], st));
             {
@@ -398,6 +420,9 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             ctx->stats.prep_ms += t;
             AH_CUDA(cudaEventElapsedTime(&t, E[1], E[2]));
             ctx->stats.bisect_ms += t;
+            ms_main += t;
+            AH_CUDA(cudaEventElapsedTime(&t, ctx->side_ev[2 * (size_t)c], ctx->side_ev[2 * (size_t)c + 1]));
+            ctx->stats.rem3_ms += t;          // runs beside k_vec: contained in the span below when vectors are wanted
             ms_main += t;
             AH_CUDA(cudaEventElapsedTime(&t, E[2], E[3]));
             ctx->stats.vec_ms += t;
@@ -566,6 +591,13 @@ int ah_create(ah_ctx **pctx, int device) {
     if ((e = cudaSetDevice(device)) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaSetDevice"); }
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
+        ok = ok && cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    }
     for (auto &ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     for (auto &ev : ctx->ev_stage) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaMallocHost((void **)&ctx->hCounts, 64 * sizeof(unsigned long long)) == cudaSuccess;
@@ -596,6 +628,10 @@ void ah_destroy(ah_ctx *ctx) {
         if (b->p) cudaFree(b->p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (auto &ev : ctx->side_ev) cudaEventDestroy(ev);
     delete ctx;
 }
 

@@ -32,10 +32,11 @@
 #include "ah_full.cuh"
 
 #include <algorithm>
+#include <cstdint>
 
 namespace ah {
 
-enum : int { KS_READY = 0, KS_HANDOFF = 1, KS_DONE = 2, KS_REM3 = 3, KS_REM3_READY = 4 };
+enum : int { KS_READY = 0, KS_HANDOFF = 1, KS_DONE = 2, KS_REM3 = 3, KS_REM3_READY = 4, KS_DONE1 = 5 };   // DONE1: finished in round 1
 // counters (unsigned long long[4]): [0] hand-over list length, [1] k_bisect round-0 work counter,
 //                                   [2] Remedy-3 list length,   [3] k_bisect round-1 work counter
 
@@ -399,7 +400,7 @@ __device__ __forceinline__ void bisect_finalize(const Problem &P, const Outputs 
             rlist[atomicAdd(dcount + 2, 1ull)] = S.k;
         } else {
             G.nu = nu; G.mu = mu; G.lambda = lambda; G.knu = Knu; G.steps = S.steps;
-            G.flag = KS_DONE;
+            G.flag = (ROUND == 0) ? KS_DONE : KS_DONE1;
             O.lambda[col] = lambda;
             O.sind[col] = S.i;
             O.kb[col] = S.Kb; O.kz[col] = S.Kz; O.knu[col] = Knu; O.krho[col] = (ROUND == 0) ? 0.0 : S.krho;
@@ -414,10 +415,11 @@ __device__ __forceinline__ bool bisect_converged(const BSlot &S) {
     return !((S.right - S.left) > 2.0 * kEps * fmax(fabs(S.left), fabs(S.right)));
 }
 
-template <int KIND, int ROUND>
+template <int KIND, int ROUND, int NSLOT>
 __global__ void __launch_bounds__(BT, BCTAS)
 k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *__restrict__ dlist,
          int64_t *__restrict__ rlist, unsigned long long *dcount) {
+    static_assert(NSLOT >= 1 && NSLOT <= BJ && NSLOT <= BW, "one warp per slot");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BisectShared &sh = *reinterpret_cast<BisectShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -427,7 +429,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         for (int s = 0; s < BS; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], BW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < BJ) { sh.slot[tid].phase = PH_FREE; sh.skip[tid] = -1; sh.act[tid] = 0; sh.hot[tid] = make_double2(0.0, 0.0); }
+    if (tid < NSLOT) { sh.slot[tid].phase = PH_FREE; sh.skip[tid] = -1; sh.act[tid] = 0; sh.hot[tid] = make_double2(0.0, 0.0); }
     if (ROUND == 1) cnt = (int64_t)dcount[2];   // round 1 works through the Remedy-3 list
     __syncthreads();
 
@@ -450,7 +452,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
     bool first = true;
     while (true) {
         // ================= sweep boundary: warp j advances slot j =================
-        if (warp < BJ) {
+        if (warp < NSLOT) {
             BSlot &S = sh.slot[warp];
             if (!first && S.phase == PH_BISECT) {
                 double sum = (lane < BW) ? sh.part[warp][lane] : 0.0;
@@ -535,7 +537,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         unsigned fixmask = 0;
         int fmin = 0x7fffffff, fmax_ = -1;
 #pragma unroll
-        for (int j = 0; j < BJ; ++j) {
+        for (int j = 0; j < NSLOT; ++j) {
             const long long sk = sh.skip[j];
             if (sh.act[j] != 0) actmask |= 1u << j;
             if (sk >= 0) {
@@ -545,9 +547,9 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             }
         }
         if (actmask == 0) break;
-        double acc[BJ];
+        double acc[NSLOT];
 #pragma unroll
-        for (int j = 0; j < BJ; ++j) acc[j] = 0.0;
+        for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
 
         // ================= the sweep =================
         for (int tile = 0; tile < ntiles; ++tile, ++g) {
@@ -571,15 +573,15 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             const bool fix = fixmask != 0 && tile >= fmin && tile <= fmax_;
             if (fix) {
 #pragma unroll
-                for (int j = 0; j < BJ; ++j)
+                for (int j = 0; j < NSLOT; ++j)
                     if ((fixmask >> j) & 1u) sh.save[j] = acc[j];
             }
 
-            // ---- the branch-free block: BE x BJ independent 8-deep chains.  (Idle slots -- end of the work list,
+            // ---- the branch-free block: BE x NSLOT independent 8-deep chains.  (Idle slots -- end of the work list,
             // Remedy-3 round -- are evaluated on dummy parameters: skipping them with CTA-uniform branches was
             // measured and costs the full-occupancy case more than the tail gains.)
 #pragma unroll
-            for (int j = 0; j < BJ; ++j) {
+            for (int j = 0; j < NSLOT; ++j) {
                 // Round 1 has few eigenpairs (~1 %), spread thinly over the CTAs: skip idle slots there with a
                 // CTA-uniform branch.  (In round 0 the same test costs the full-occupancy loop 2-4 %: measured.)
                 if (ROUND == 0 || ((actmask >> j) & 1u)) {
@@ -593,7 +595,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             if (fix) {
                 const long long base = (long long)tile * BTL;
 #pragma unroll
-                for (int j = 0; j < BJ; ++j) {
+                for (int j = 0; j < NSLOT; ++j) {
                     if ((fixmask >> j) & 1u) {
                         const long long sk = sh.skip[j];
                         if (sk / BTL == tile) {
@@ -612,7 +614,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
 
         // ================= reduce this sweep's partial sums =================
 #pragma unroll
-        for (int j = 0; j < BJ; ++j) {
+        for (int j = 0; j < NSLOT; ++j) {
             const double v = warp_allreduce(acc[j], OpSum());
             if (lane == 0) sh.part[j][warp] = v;
         }
@@ -690,25 +692,33 @@ constexpr int VT = 256, VW = VT / 32, VJ = 4;
 
 template <int KIND>
 __global__ void __launch_bounds__(VT, 2)
-k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_t cnt) {
+k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_t cnt, const int64_t *__restrict__ klist,
+      const unsigned long long *nlist_dev, int want_flag) {
+    // dense mode (klist == nullptr): group g = eigenpairs kbase + VJ*g .. +VJ-1 with flag == want_flag (the ones round 0
+    // finished); list mode: the eigenpairs of klist (the Remedy-3 list, finished by round 1), grid-stride over groups.
     __shared__ double red[VJ][VW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t N = P.N, Np = P.Np;
     const double *__restrict__ D = P.D;
     const double *__restrict__ W = P.w;
-    const int64_t c0 = (int64_t)blockIdx.x * VJ;
+    const int64_t nitems = klist ? (int64_t)*nlist_dev : cnt;
+    for (int64_t c0 = (int64_t)blockIdx.x * VJ; c0 < nitems; c0 += (int64_t)gridDim.x * VJ) {
+    if (c0 != (int64_t)blockIdx.x * VJ) __syncthreads();    // red[] is reused
 
     bool valid[VJ];
+    int64_t cix[VJ];                                         // index of the eigenpair within the block (k - kbase)
     double sigma[VJ], mu[VJ], lambda[VJ];
     bool any = false;
 #pragma unroll
     for (int j = 0; j < VJ; ++j) {
-        valid[j] = (c0 + j < cnt) && ks[c0 + j].flag == KS_DONE;
+        valid[j] = c0 + j < nitems;
+        cix[j] = valid[j] ? (klist ? klist[c0 + j] - kbase : c0 + j) : 0;
+        valid[j] = valid[j] && ks[cix[j]].flag == want_flag;
         any = any || valid[j];
-        if (valid[j]) { sigma[j] = ks[c0 + j].sigma; mu[j] = ks[c0 + j].mu; lambda[j] = ks[c0 + j].lambda; }
+        if (valid[j]) { sigma[j] = ks[cix[j]].sigma; mu[j] = ks[cix[j]].mu; lambda[j] = ks[cix[j]].lambda; }
         else { sigma[j] = 0.0; mu[j] = -1.0e300; lambda[j] = 1.0; }
     }
-    if (!any) return;
+    if (!any) continue;
 
     // ---- VNORM (the norm is a sum over N entries: <=1-ulp reciprocal; the entries themselves are divided exactly below)
     double ss[VJ];
@@ -752,8 +762,8 @@ k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_
     double *ucol[VJ], *vcol[VJ];
 #pragma unroll
     for (int j = 0; j < VJ; ++j) {
-        const int64_t k = kbase + c0 + j;
-        const int64_t colidx = (valid[j] && umap) ? umap[k - 1] : c0 + j;
+        const int64_t k = kbase + cix[j];
+        const int64_t colidx = (valid[j] && umap) ? umap[k - 1] : cix[j];
         ucol[j] = (valid[j] && O.U) ? O.U + colidx * O.ldu : nullptr;
         vcol[j] = (KIND == KIND_HALF && valid[j] && O.V) ? O.V + colidx * O.ldv : nullptr;
     }
@@ -803,16 +813,31 @@ k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_
             if (KIND == KIND_HALF && ucol[j] && P.has_tip) ucol[j][umap ? umap[N] : N] = __ddiv_rn(__dmul_rn(P.ztip, vt), lambda[j]);
         }
     }
+    }   // groups
 }
 
 // =====================================================================================================
+// Slots per CTA for round 0.  All NSLOT slots of a CTA are evaluated in every sweep, so a launch costs about
+// waves * NSLOT sweeps-worth of work with waves = ceil(cnt / (CTAs * NSLOT)): for small k-ranges (multi-GPU
+// shards, host-staged column blocks) 7 or 6 slots can pack the eigenpairs into fuller waves than 8.
+inline int pick_slots(int64_t cnt, int64_t ctas) {
+    int best = BJ;
+    int64_t best_cost = INT64_MAX;
+    for (int ns = BJ; ns >= BJ - 2; --ns) {
+        const int64_t waves = (cnt + ctas * ns - 1) / (ctas * ns);
+        const int64_t cost = waves * ns * 16 + (BJ - ns);          // tie -> more slots (less L2 traffic per term)
+        if (cost < best_cost) { best_cost = cost; best = ns; }
+    }
+    return best;
+}
+
 inline int configure_pipe_kernels() {
     const int smem = (int)sizeof(BisectShared);
     cudaError_t e;
 #define AH_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)e
-    AH_SET_SMEM((k_bisect<KIND_ARROW, 0>)); AH_SET_SMEM((k_bisect<KIND_ARROW, 1>));
-    AH_SET_SMEM((k_bisect<KIND_DPR1, 0>));  AH_SET_SMEM((k_bisect<KIND_DPR1, 1>));
-    AH_SET_SMEM((k_bisect<KIND_HALF, 0>));  AH_SET_SMEM((k_bisect<KIND_HALF, 1>));
+#define AH_SET_KIND(KD) AH_SET_SMEM((k_bisect<KD, 0, 8>)); AH_SET_SMEM((k_bisect<KD, 0, 7>)); AH_SET_SMEM((k_bisect<KD, 0, 6>)); AH_SET_SMEM((k_bisect<KD, 1, 8>))
+    AH_SET_KIND(KIND_ARROW); AH_SET_KIND(KIND_DPR1); AH_SET_KIND(KIND_HALF);
+#undef AH_SET_KIND
 #undef AH_SET_SMEM
     return 0;
 }
@@ -829,25 +854,26 @@ inline int launch_prep(int kind, const Problem &P, KState *ks, int64_t kbase, in
     return (int)cudaGetLastError();
 }
 // round 0: all READY eigenpairs of the block; round 1: the Remedy-3 list (its length is read on the device)
+template <int KIND>
+inline void launch_bisect_kind(int round, int nslot, int grid, int smem, cudaStream_t st, const Problem &P, const Outputs &O, KState *ks,
+                               int64_t kbase, int64_t cnt, int64_t *dlist, int64_t *rlist, unsigned long long *dcount) {
+    if (round == 1) k_bisect<KIND, 1, 8><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount);
+    else if (nslot == 8) k_bisect<KIND, 0, 8><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount);
+    else if (nslot == 7) k_bisect<KIND, 0, 7><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount);
+    else k_bisect<KIND, 0, 6><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount);
+}
 inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O, KState *ks, int64_t kbase, int64_t cnt,
                          int64_t *dlist, int64_t *rlist, unsigned long long *dcount, int sm_count, cudaStream_t st) {
     const int smem = (int)sizeof(BisectShared);
-    // one CTA per SM, but never more CTAs than there are groups of BJ eigenpairs
-    const int64_t want = (round == 1) ? cnt : (cnt + BJ - 1) / BJ;   // round 1: one eigenpair per CTA where possible
     const int64_t cap = (int64_t)sm_count * BCTAS;
-    int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-    if (round == 0) {
-        switch (kind) {
-            case KIND_ARROW: k_bisect<KIND_ARROW, 0><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
-            case KIND_DPR1: k_bisect<KIND_DPR1, 0><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
-            default: k_bisect<KIND_HALF, 0><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
-        }
-    } else {
-        switch (kind) {
-            case KIND_ARROW: k_bisect<KIND_ARROW, 1><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
-            case KIND_DPR1: k_bisect<KIND_DPR1, 1><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
-            default: k_bisect<KIND_HALF, 1><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
-        }
+    const int nslot = (round == 1) ? BJ : pick_slots(cnt, cap);
+    // one CTA per SM slot, but never more CTAs than there are groups of eigenpairs (round 1: one eigenpair per CTA where possible)
+    const int64_t want = (round == 1) ? cnt : (cnt + nslot - 1) / nslot;
+    const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    switch (kind) {
+        case KIND_ARROW: launch_bisect_kind<KIND_ARROW>(round, nslot, grid, smem, st, P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
+        case KIND_DPR1: launch_bisect_kind<KIND_DPR1>(round, nslot, grid, smem, st, P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
+        default: launch_bisect_kind<KIND_HALF>(round, nslot, grid, smem, st, P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
     }
     return (int)cudaGetLastError();
 }
@@ -861,13 +887,16 @@ inline int launch_rem3_prep(int kind, const Problem &P, KState *ks, int64_t kbas
     }
     return (int)cudaGetLastError();
 }
+// klist == nullptr: the eigenpairs round 0 finished (flag KS_DONE); else the Remedy-3 list (flag KS_DONE1, length on the device)
 inline int launch_vec(int kind, const Problem &P, const Outputs &O, const KState *ks, int64_t kbase, int64_t cnt,
-                      cudaStream_t st) {
-    const int grid = (int)((cnt + VJ - 1) / VJ);
+                      const int64_t *klist, const unsigned long long *nlist_dev, int sm_count, cudaStream_t st) {
+    int grid = (int)((cnt + VJ - 1) / VJ);
+    if (klist) grid = (int)std::min<int64_t>(grid, (int64_t)sm_count * 2);
+    const int flag = klist ? KS_DONE1 : KS_DONE;
     switch (kind) {
-        case KIND_ARROW: k_vec<KIND_ARROW><<<grid, VT, 0, st>>>(P, O, ks, kbase, cnt); break;
-        case KIND_DPR1: k_vec<KIND_DPR1><<<grid, VT, 0, st>>>(P, O, ks, kbase, cnt); break;
-        default: k_vec<KIND_HALF><<<grid, VT, 0, st>>>(P, O, ks, kbase, cnt); break;
+        case KIND_ARROW: k_vec<KIND_ARROW><<<grid, VT, 0, st>>>(P, O, ks, kbase, cnt, klist, nlist_dev, flag); break;
+        case KIND_DPR1: k_vec<KIND_DPR1><<<grid, VT, 0, st>>>(P, O, ks, kbase, cnt, klist, nlist_dev, flag); break;
+        default: k_vec<KIND_HALF><<<grid, VT, 0, st>>>(P, O, ks, kbase, cnt, klist, nlist_dev, flag); break;
     }
     return (int)cudaGetLastError();
 }

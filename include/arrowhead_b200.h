@@ -90,7 +90,7 @@ typedef struct ah_result {
 /* timing + accounting of the last compute call on a context */
 typedef struct ah_stats {
     double  kernel_ms;        /* device time of all kernels of the call (CUDA events on the context stream) */
-    double  main_kernel_ms;   /* device time of the dominant kernel (k_bisect) alone */
+    double  main_kernel_ms;   /* device time of the dominant kernel: k_bisect round 0 (bisect_ms) + round 1 (rem3_ms) */
     double  h2d_ms, d2h_ms;   /* host<->device copies issued by the call */
     int64_t launches;         /* number of kernels launched by the call */
     int64_t n_fast;           /* eigenpairs finished by the fast-path kernels (k_prep -> k_bisect -> k_vec) */
@@ -99,6 +99,7 @@ typedef struct ah_stats {
     int64_t h2d_bytes, d2h_bytes;
     double  prep_ms, bisect_ms, vec_ms, full_ms;   /* per-kernel device time: k_prep, k_bisect (+ Remedy-3 round), k_vec, k_full */
     int64_t n_rem3;           /* eigenpairs that took the Remedy-3 round of the fast path (counted in n_fast) */
+    double  rem3_ms;          /* k_rem3_prep + k_bisect round 1 (device time on the side stream; overlaps k_vec) */
 } ah_stats;
 
 /* ---- context ---------------------------------------------------------------------------------- */
