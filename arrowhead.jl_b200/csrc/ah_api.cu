@@ -148,6 +148,7 @@ int validate_common(ah_ctx *ctx, int64_t N, const double *D, const double *w, in
     if (!ctx) return AH_ERR_INVALID_ARG;
     if (!D || !w || !out || !out->lambda) return fail(ctx, AH_ERR_INVALID_ARG, "null argument");
     if (N < 1) return fail(ctx, AH_ERR_INVALID_ARG, "need at least one pole");
+    if (N > (int64_t)1 << 30) return fail(ctx, AH_ERR_INVALID_ARG, "more than 2^30 poles");
     if (k0 < 1 || k1 < k0 || k1 > kmax) return fail(ctx, AH_ERR_INVALID_ARG, "k-range outside 1.." + std::to_string(kmax));
     for (int64_t l = 0; l < N; ++l) {
         if (!std::isfinite(D[l])) return fail(ctx, AH_ERR_NOT_ORDERED, "non-finite pole");

@@ -131,9 +131,9 @@ k_prep(Problem P, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *
 #pragma unroll
     for (int j = 0; j < PJ; ++j) xs[j] = 0.0;
     double2 d2n = ldg2(D + 2 * tid), w2n = ldg2(W + 2 * tid);
-    for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * PT) {
+    for (int l0 = 2 * tid; l0 < (int)Np; l0 += 2 * PT) {
         const double2 d2 = d2n, w2 = w2n;
-        if (l0 + 2 * PT < Np) { d2n = ldg2(D + l0 + 2 * PT); w2n = ldg2(W + l0 + 2 * PT); }   // prefetch the next pair
+        if (l0 + 2 * PT < (int)Np) { d2n = ldg2(D + l0 + 2 * PT); w2n = ldg2(W + l0 + 2 * PT); }   // prefetch the next pair
         const double dv[2] = {d2.x, d2.y};
         const double w2v[2] = {__dmul_rn(w2.x, w2.x), __dmul_rn(w2.y, w2.y)};
 #pragma unroll
@@ -180,19 +180,23 @@ k_prep(Problem P, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *
 #pragma unroll
     for (int j = 0; j < PJ; ++j) { a0[j] = 0.0; a1[j] = 0.0; a2[j] = 0.0; a3[j] = -INFINITY; a4[j] = 0.0; }
     d2n = ldg2(D + 2 * tid); w2n = ldg2(W + 2 * tid);
-    for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * PT) {
+    int iis[PJ];                                           // 32-bit copies: the sweep index fits (N < 2^31 is checked on the host)
+#pragma unroll
+    for (int j = 0; j < PJ; ++j) iis[j] = (int)ii[j];
+    const int Ni = (int)N, Npi = (int)Np;
+    for (int l0 = 2 * tid; l0 < Npi; l0 += 2 * PT) {
         const double2 d2 = d2n, w2 = w2n;
-        if (l0 + 2 * PT < Np) { d2n = ldg2(D + l0 + 2 * PT); w2n = ldg2(W + l0 + 2 * PT); }   // prefetch the next pair
+        if (l0 + 2 * PT < Npi) { d2n = ldg2(D + l0 + 2 * PT); w2n = ldg2(W + l0 + 2 * PT); }   // prefetch the next pair
         const double dv[2] = {d2.x, d2.y};
         const double wv[2] = {w2.x, w2.y};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int64_t l = l0 + h;
+            const int l = l0 + h;
             const double W2 = __dmul_rn(wv[h], wv[h]);
-            if (l < N) {
+            if (l < Ni) {
 #pragma unroll
                 for (int j = 0; j < PJ; ++j) {
-                    if (l != ii[j]) {
+                    if (l != iis[j]) {
                         const double Dp = rcp_fast(dshift<KIND>(dv[h], sigma[j]));   // feeds sums and maxima over N entries only
                         const double zp = __dmul_rn(__dmul_rn(-wv[h], Dp), wz[j]);
                         const double t = __dmul_rn(W2, Dp);
@@ -725,14 +729,15 @@ k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_
 #pragma unroll
     for (int j = 0; j < VJ; ++j) ss[j] = 0.0;
     double2 d2n = ldg2(D + 2 * tid), w2n = ldg2(W + 2 * tid);
-    for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * VT) {
+    const int Ni = (int)N, Npi = (int)Np;
+    for (int l0 = 2 * tid; l0 < Npi; l0 += 2 * VT) {
         const double2 d2 = d2n, w2 = w2n;
-        if (l0 + 2 * VT < Np) { d2n = ldg2(D + l0 + 2 * VT); w2n = ldg2(W + l0 + 2 * VT); }   // prefetch the next pair
+        if (l0 + 2 * VT < Npi) { d2n = ldg2(D + l0 + 2 * VT); w2n = ldg2(W + l0 + 2 * VT); }   // prefetch the next pair
         const double dv[2] = {d2.x, d2.y};
         const double wv[2] = {w2.x, w2.y};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            if (l0 + h < N) {
+            if (l0 + h < Ni) {
 #pragma unroll
                 for (int j = 0; j < VJ; ++j) {
                     const double v = __dmul_rn(wv[h], rcp_fast(__dadd_rn(dshift<KIND>(dv[h], sigma[j]), -mu[j])));
@@ -768,6 +773,29 @@ k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_
         vcol[j] = (KIND == KIND_HALF && valid[j] && O.V) ? O.V + colidx * O.ldv : nullptr;
     }
     d2n = ldg2(D + 2 * tid); w2n = ldg2(W + 2 * tid);
+    if (KIND != KIND_HALF && !umap) {
+        // common case (no deflation row map): per-column store mode decided once -- 0: skip, 1: 16-byte stores (column
+        // start 16-byte aligned; l0 is even), 2: two 8-byte stores (odd leading dimension -> every other column)
+        int mode[VJ];
+#pragma unroll
+        for (int j = 0; j < VJ; ++j) mode[j] = !ucol[j] ? 0 : (((reinterpret_cast<uintptr_t>(ucol[j]) & 15) == 0) ? 1 : 2);
+        for (int l0 = 2 * tid; l0 < Ni; l0 += 2 * VT) {
+            const double2 d2 = d2n, w2 = w2n;
+            if (l0 + 2 * VT < Npi) { d2n = ldg2(D + l0 + 2 * VT); w2n = ldg2(W + l0 + 2 * VT); }
+            const bool pair = l0 + 1 < Ni;
+#pragma unroll
+            for (int j = 0; j < VJ; ++j) {
+                const double v0 = __dmul_rn(__ddiv_rn(w2.x, __dadd_rn(dshift<KIND>(d2.x, sigma[j]), -mu[j])), inrm[j]);
+                const double v1 = __dmul_rn(__ddiv_rn(w2.y, __dadd_rn(dshift<KIND>(d2.y, sigma[j]), -mu[j])), inrm[j]);
+                if (mode[j] == 1 && pair) {
+                    *reinterpret_cast<double2 *>(ucol[j] + l0) = make_double2(v0, v1);
+                } else if (mode[j] != 0) {
+                    ucol[j][l0] = v0;
+                    if (pair) ucol[j][l0 + 1] = v1;
+                }
+            }
+        }
+    } else
     for (int64_t l0 = 2 * tid; l0 < Np; l0 += 2 * VT) {
         if (l0 >= N) break;
         const double2 d2 = d2n, w2 = w2n;

@@ -200,12 +200,13 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     launches = 0
-    kern_ms = main_ms = 0.0
+    kern_ms = main_ms = vec_ms = 0.0
     for _ in range(args.steps):
         res = step()
         launches += res.stats["launches"]
         kern_ms += res.stats["kernel_ms"]
         main_ms += res.stats["main_kernel_ms"]
+        vec_ms += res.stats["vec_ms"]
     ev1.record()
     torch.cuda.synchronize()
     sampler.stop_flag = True
@@ -226,7 +227,7 @@ def run_ours(args):
     N = n - 1
     fast = res.status == 0            # (k_full's few eigenpairs are included: their first bisection ran in k_bisect)
     n_fast = res.stats["n_fast"]
-    terms_fast = float(res.steps[fast].astype(np.float64).sum()) * N   # k_bisect: one sweep of N secular terms per bisection step
+    terms_fast = float(res.steps[fast].astype(np.float64).sum()) * N   # k_bisect (both rounds): one sweep of N secular terms per bisection step
     t_main = main_ms / args.steps * 1e-3
     instr_rate = FP64_INSTR_PER_TERM * terms_fast / t_main / 1e9       # G lane-instructions/s
     achieved_tf = 2.0 * instr_rate / 1e3
@@ -237,15 +238,21 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_achieved = cnt * n * 8 / t_main / 1e9
+    hbm_achieved = cnt * n * 8 / (vec_ms / args.steps * 1e-3) / 1e9    # U is written by k_vec (its span also hosts the Remedy-3 round)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj["k_bisect_round0"]["dram_bytes_per_launch"] if n == tj.get("n") and world == 1 else None
+    except Exception:
+        pass
     roofline = {
         "bound": "fp64", "kernel": "k_bisect<SymArrow> (round 0 + Remedy-3 round 1)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": achieved_tf / peak_tf, "traffic": None,
+        "frac": achieved_tf / peak_tf, "traffic": traffic,
         "how": "FP64-pipe lane-instructions x2 (FMA-equivalent); 7 per secular term x steps_k x N terms per "
-               "fast-path eigenpair / mean k_bisect duration (CUDA events around the launch, inside the timed "
-               "region); peak = dependent-free DFMA burst measured live (MEASURED_PEAKS.json has no FP64 entry)",
+               "eigenpair / device time of k_bisect (round 0 + the Remedy-3 round, CUDA events on their streams inside "
+               "the timed region); peak = dependent-free DFMA burst measured live (MEASURED_PEAKS.json has no FP64 entry)",
         "terms_per_launch": terms_fast, "kernel_ms": t_main * 1e3, "fast_eigenpairs": int(n_fast),
-        "hbm_store": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+        "hbm_store": {"kernel": "k_vec", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                       "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "alt_frac_10_instr_per_term": 10.0 / FP64_INSTR_PER_TERM * achieved_tf / peak_tf,
     }
@@ -317,7 +324,7 @@ def run_ours(args):
                        "l2": "256 MB flush write before every step; the step itself streams out n^2*8 bytes >> L2",
                        "allgather_U_ms": allgather_ms,
                        "kernel_ms_per_step_rank0": kern_ms / args.steps,
-                       "kernel_ms_breakdown_rank0": {k: res.stats[k] for k in ("prep_ms", "bisect_ms", "vec_ms", "full_ms")},
+                       "kernel_ms_breakdown_rank0": {k: res.stats[k] for k in ("prep_ms", "bisect_ms", "rem3_ms", "vec_ms", "full_ms")},
                        "n_full_rank0": int(res.stats["n_full"]), "n_rem3_rank0": int(res.stats["n_rem3"]),
                        "total_steps_rank0": int(res.stats["total_steps"])},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
