@@ -330,7 +330,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                     AH_CUDA(cudaStreamWaitEvent(rs, ctx->ev_fork, 0));
                 }
                 AH_CUDA(cudaEventRecord(SE[0], rs));
-                rc = ah::launch_rem3_prep(L.kind, P, ks, kb, guess, rlist, dlist, dcount, ctx->sm_count, rs);
+                rc = ah::launch_rem3_prep(L.kind, P, Oc, ks, kb, guess, rlist, dlist, dcount, ctx->sm_count, rs);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_rem3_prep launch");
                 rc = ah::launch_bisect(L.kind, 1, P, Oc, ks, kb, guess, dlist, rlist, dcount, ctx->sm_count, rs);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect round 1 launch");

@@ -301,6 +301,7 @@ constexpr int BTL = BT * BE;     // poles per tile (2048)
 #define AH_BS 4
 #endif
 constexpr int BS = AH_BS;        // ring stages
+constexpr int REM3_DIRECT_MAX = 128;   // Remedy-3 lists up to this length are bisected by k_rem3_prep itself, one CTA per eigenpair
 constexpr int TILE_POLES = 2048; // inputs are padded to a multiple of this (a multiple of BTL)
 static_assert(TILE_POLES % BTL == 0, "tile size");
 static_assert((BS & (BS - 1)) == 0, "ring depth must be a power of two (stage = g & (BS-1); measured: BS = 3, 5, 6 cost 7 % in index arithmetic, BS = 2 and 4 perform alike)");
@@ -436,6 +437,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
     if (tid < NSLOT) { sh.slot[tid].phase = PH_FREE; sh.skip[tid] = -1; sh.act[tid] = 0; sh.hot[tid] = make_double2(0.0, 0.0); }
     if (ROUND == 1) cnt = (int64_t)dcount[2];   // round 1 works through the Remedy-3 list
     __syncthreads();
+    if (ROUND == 1 && cnt <= REM3_DIRECT_MAX) return;   // short list: k_rem3_prep has bisected it directly
 
     bool wrapped = false;    // g_issue has wrapped around 2^32 at least once
     uint32_t g_issue = 0;    // tiles issued (thread 0 only); wraps mod 2^32, a multiple of 2*BS -> parities stay consistent
@@ -638,13 +640,22 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
 // eigenpair (~1 % of all).  Anything beyond the plain binary64 branch (sigma_1 hits a pole, double-double rho)
 // is handed to k_full.
 constexpr int RT = 256;
+static_assert(RT == BT, "the direct bisection reproduces k_bisect's summation order thread by thread");
 
 template <int KIND>
 __global__ void __launch_bounds__(RT)
-k_rem3_prep(Problem P, KState *__restrict__ ks, int64_t kbase, const int64_t *__restrict__ rlist, int64_t *__restrict__ dlist,
+k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t *__restrict__ rlist, int64_t *__restrict__ dlist,
             unsigned long long *dcount) {
     __shared__ double red[2 * (RT / 32) + 2];
+    __shared__ double part2[2][RT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nwork = (int64_t)dcount[2];
+    // Short lists (small k-ranges: multi-GPU shards, host-staged blocks): the persistent 8-slot kernel would spend a
+    // whole latency-bound wave on a handful of eigenpairs, so each CTA bisects its eigenpair itself with plain
+    // global loads -- in EXACTLY k_bisect's summation order (same thread -> pole map, same reduction trees), so the
+    // result does not depend on which of the two ways was taken (bitwise shard-invariance is tested).
+    const bool direct = nwork <= REM3_DIRECT_MAX;
+    const int ntiles = (int)(P.Np / BTL);
     for (int64_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
         const int64_t k = rlist[wi];
         KState &G = ks[k - kbase];
@@ -665,26 +676,69 @@ k_rem3_prep(Problem P, KState *__restrict__ ks, int64_t kbase, const int64_t *__
             inv_at_value<KIND, RT>(P, shift, P.tau[3], R, status, red);
             full = (R.Qout != 0) || (status != 0) || !isfinite(R.rho);
         }
-        if (threadIdx.x == 0) {
-            if (full) {
+        double left = 0.0, right = 0.0, nu1new = 0.0;
+        if (!full) {
+            const double ruu = __dmul_rn(R.rho, R.uu);   // bracket of bisect(::SymDPR1,side), arrowhead3.jl:722-726
+            if (R.rho > 0.0) {
+                if (!sideR) { left = R.mn1; right = R.mn2; }
+                else { left = R.mx1; right = __dadd_rn(R.mx1, ruu); }
+            } else {
+                if (!sideR) { left = __dadd_rn(R.mn1, ruu); right = R.mn1; }
+                else { left = R.mx2; right = R.mx1; }
+            }
+            nu1new = __dadd_rn(R.maxabsD, __dmul_rn(fabs(R.rho), R.uu));
+        }
+        if (full) {
+            if (tid == 0) {
                 G.flag = KS_HANDOFF;
                 dlist[atomicAdd(dcount, 1ull)] = k;
-            } else {
-                const double ruu = __dmul_rn(R.rho, R.uu);
-                double left, right;   // bracket of bisect(::SymDPR1,side), arrowhead3.jl:722-726
-                if (R.rho > 0.0) {
-                    if (!sideR) { left = R.mn1; right = R.mn2; }
-                    else { left = R.mx1; right = __dadd_rn(R.mx1, ruu); }
-                } else {
-                    if (!sideR) { left = __dadd_rn(R.mn1, ruu); right = R.mn1; }
-                    else { left = R.mx2; right = R.mx1; }
-                }
+            }
+        } else if (!direct) {
+            if (tid == 0) {
                 G.sigma = shift; G.b = R.rho; G.krho = R.Krho;
                 G.left = left; G.right = right;
-                G.nu1 = __dadd_rn(R.maxabsD, __dmul_rn(fabs(R.rho), R.uu));
+                G.nu1 = nu1new;
                 G.lambda = sigma1;
                 G.flag = KS_REM3_READY;
             }
+        } else {
+            BSlot S;                                   // identical copy in every thread
+            S.k = k; S.i = G.i; S.phase = PH_BISECT; S.sideR = sideR ? 1 : 0; S.steps = G.steps; S.pad_ = 0;
+            S.sigma = shift; S.wz2 = 1.0; S.b = R.rho; S.left = left; S.right = right; S.m = (left + right) / 2.0;
+            S.nu1 = nu1new; S.Kb = G.Kb; S.Kz = G.Kz; S.knu0 = G.knu; S.krho = R.Krho; S.sig2 = sigma1;
+            __syncthreads();                           // every thread has read G before thread 0 rewrites it in the finalize
+            int par = 0;
+            while (!bisect_converged(S)) {
+                double acc = 0.0;
+                for (int tile = 0; tile < ntiles; ++tile) {
+                    const double *Dt = P.D + (int64_t)tile * BTL, *Wt = P.w2 + (int64_t)tile * BTL;
+#pragma unroll
+                    for (int e = 0; e < BE; e += 2) {
+                        const double2 d2 = ldg2(Dt + elem_offset(tid, e)), w2 = ldg2(Wt + elem_offset(tid, e));
+                        acc = secular_term_acc(acc, dshift<KIND>(d2.x, S.sigma), S.m, w2.x);
+                        acc = secular_term_acc(acc, dshift<KIND>(d2.y, S.sigma), S.m, w2.y);
+                    }
+                }
+                const double v = warp_allreduce(acc, OpSum());
+                if (lane == 0) part2[par][warp] = v;
+                __syncthreads();
+                double sum = (lane < BW) ? part2[par][lane] : 0.0;
+#pragma unroll
+                for (int o = BW / 2; o > 0; o >>= 1) {
+                    const double p = __shfl_xor_sync(0xffffffffu, sum, o);
+                    sum = (lane & o) ? __dadd_rn(p, sum) : __dadd_rn(sum, p);
+                }
+                sum = __shfl_sync(0xffffffffu, sum, 0);
+                const double m = S.m;
+                if (KIND != KIND_DPR1) sum = __dadd_rn(sum, __ddiv_rn(1.0, __dadd_rn(0.0, -m)));
+                const double F = __dadd_rn(1.0, __dmul_rn(S.b, sum));
+                if (sign_jl(S.b) * F < 0.0) S.left = m; else S.right = m;
+                S.m = (S.left + S.right) / 2.0;
+                S.steps += 1;
+                par ^= 1;
+            }
+            if (tid == 0) { G.sigma = shift; G.krho = R.Krho; }   // k_vec reads sigma (the new shift), mu, lambda
+            bisect_finalize<KIND, 1>(P, O, ks, S, kbase, dlist, rlist, dcount, tid == 0 ? 0 : 1);
         }
         __syncthreads();
     }
@@ -905,13 +959,13 @@ inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O
     }
     return (int)cudaGetLastError();
 }
-inline int launch_rem3_prep(int kind, const Problem &P, KState *ks, int64_t kbase, int64_t cnt, const int64_t *rlist,
+inline int launch_rem3_prep(int kind, const Problem &P, const Outputs &O, KState *ks, int64_t kbase, int64_t cnt, int64_t *rlist,
                             int64_t *dlist, unsigned long long *dcount, int sm_count, cudaStream_t st) {
     const int grid = (int)std::min<int64_t>(cnt, (int64_t)sm_count * 4);
     switch (kind) {
-        case KIND_ARROW: k_rem3_prep<KIND_ARROW><<<grid, RT, 0, st>>>(P, ks, kbase, rlist, dlist, dcount); break;
-        case KIND_DPR1: k_rem3_prep<KIND_DPR1><<<grid, RT, 0, st>>>(P, ks, kbase, rlist, dlist, dcount); break;
-        default: k_rem3_prep<KIND_HALF><<<grid, RT, 0, st>>>(P, ks, kbase, rlist, dlist, dcount); break;
+        case KIND_ARROW: k_rem3_prep<KIND_ARROW><<<grid, RT, 0, st>>>(P, O, ks, kbase, rlist, dlist, dcount); break;
+        case KIND_DPR1: k_rem3_prep<KIND_DPR1><<<grid, RT, 0, st>>>(P, O, ks, kbase, rlist, dlist, dcount); break;
+        default: k_rem3_prep<KIND_HALF><<<grid, RT, 0, st>>>(P, O, ks, kbase, rlist, dlist, dcount); break;
     }
     return (int)cudaGetLastError();
 }

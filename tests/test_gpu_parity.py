@@ -506,3 +506,26 @@ def test_tdc_device_wilkinson_w21_and_duplicate_deflation(gpu_ctx, golden):
     Eref = ab.tdc_device(dv, ev, ctx=gpu_ctx)
     Rref = ab.tdc_recursive(dv, ev, ctx=gpu_ctx)
     assert np.max(np.abs(np.sort(Eref.values) - np.sort(Rref.values))) <= 50 * EPS
+
+
+def test_remedy3_direct_and_ring_paths_agree_bitwise(gpu_ctx):
+    """Short Remedy-3 lists are bisected by k_rem3_prep itself, long ones by round 1 of the persistent kernel; both
+    use the same summation order, so sharding a problem (short lists) must reproduce the unsharded run (long list)."""
+    import torch
+    n = 14000
+    D, z, a = gen_symarrow(n, seed=421)
+    U = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    full = gpu_ctx.symarrow(D, z, a, vectors=False, U_dev=U.data_ptr(), ldu=n)
+    assert full.stats["n_rem3"] > 128                                    # ring path
+    rem = np.flatnonzero(full.krho != 0)
+    for r in range(4):
+        k0, k1 = ab.k_partition(n, 4, r)
+        Up = torch.empty((k1 - k0 + 1, n), dtype=torch.float64, device="cuda")
+        part = gpu_ctx.symarrow(D, z, a, k0=k0, k1=k1, vectors=False, U_dev=Up.data_ptr(), ldu=n)
+        assert 0 < part.stats["n_rem3"] <= 128                           # direct path
+        assert np.array_equal(part.lam, full.lam[k0 - 1:k1]) and np.array_equal(part.knu, full.knu[k0 - 1:k1])
+        assert np.array_equal(part.steps, full.steps[k0 - 1:k1])
+        cols = rem[(rem >= k0 - 1) & (rem < k1)]
+        assert cols.size > 0
+        assert torch.equal(Up[torch.as_tensor(cols - (k0 - 1), device="cuda")], U[torch.as_tensor(cols, device="cuda")])
+        del Up
