@@ -11,7 +11,7 @@ from .types import (SVD, Eigen, GenHalfArrow, GenHermArrow, GenHermDPR1, GenSymA
                     HermArrow, HermDPR1, Info, SymArrow,
                     SymDPR1)
 from ._lib import (LIB_PATH, ArrowheadError, Context, get_context, load_library, EXPORTS,  # noqa: F401
-                   ST_NU_INF, ST_NEEDS_BIGFLOAT, ST_POLE_RETURN, ST_REF_THROWS, ST_ITER_LIMIT)
+                   ST_NU_INF, ST_NEEDS_BIGFLOAT, ST_POLE_RETURN, ST_REF_THROWS, ST_ITER_LIMIT, ST_INTERLACE)
 from .drivers import (DeviceMatrix, eigen, eigen_hermarrow, eigen_hermdpr1, eigen_symarrow, eigen_symdpr1, givens, jl_sortperm_desc,  # noqa: F401
                       svd, svd_halfarrow, tdc, tdc_device, tdc_recursive)
 from .sharding import k_partition, solve_sharded  # noqa: F401

@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ARROWHEAD_B200_LIB") or os.path.join(_PKG, "libarrowhead_b200.so")   # env: A/B builds only
 
 AH_MEM_HOST, AH_MEM_DEVICE = 0, 1
-ST_NU_INF, ST_NEEDS_BIGFLOAT, ST_POLE_RETURN, ST_REF_THROWS, ST_ITER_LIMIT = 1, 2, 4, 8, 16
+ST_NU_INF, ST_NEEDS_BIGFLOAT, ST_POLE_RETURN, ST_REF_THROWS, ST_ITER_LIMIT, ST_INTERLACE = 1, 2, 4, 8, 16, 32
 
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)

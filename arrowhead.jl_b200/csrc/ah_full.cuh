@@ -62,6 +62,18 @@ __device__ __forceinline__ double dshift(double Dl, double s) {
 }
 __device__ __forceinline__ double sign_jl(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : x); }
 
+// Cauchy interlacing: eigenvalue k (descending) of an irreducible arrow / DPR1 (rho > 0) / the k-th singular
+// value of a half-arrow lies in [D_k, D_{k-1}] (D_0 = +inf, D_{N+1} = -inf).  The reference does not test this;
+// its two-stage scheme (nu from the inverse at a pole, then Remedy 3 from that nu) can return an eigenvalue of
+// the wrong end of the spectrum when the first stage is pure rounding noise (K_nu ~ 1/eps), so a violated
+// bound is reported to the caller (AH_ST_INTERLACE) instead of passing silently.
+__device__ __forceinline__ bool interlace_ok(const double *D, int64_t N, int64_t k, double lambda) {
+    if (!(lambda == lambda)) return false;
+    if (k <= N && lambda < D[k - 1]) return false;
+    if (k >= 2 && lambda > D[k - 2]) return false;
+    return true;
+}
+
 // merge two (best, second-best) pairs; MAXI: maxima, else minima
 template <bool MAXI>
 __device__ __forceinline__ void top2_merge(double &a1, double &a2, double b1, double b2) {
@@ -584,6 +596,7 @@ __device__ void solve_full(const Problem &P, const Outputs &O, int64_t k, int64_
             }
         }
     }
+    if (!(status & 1) && !interlace_ok(D, N, k, lambda)) status |= 32;   // AH_ST_INTERLACE
     if (tid == 0) {
         O.lambda[col] = lambda;
         O.sind[col] = i;

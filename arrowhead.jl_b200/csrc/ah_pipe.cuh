@@ -301,7 +301,10 @@ constexpr int BTL = BT * BE;     // poles per tile (2048)
 #define AH_BS 4
 #endif
 constexpr int BS = AH_BS;        // ring stages
-constexpr int REM3_DIRECT_MAX = 128;   // Remedy-3 lists up to this length are bisected by k_rem3_prep itself, one CTA per eigenpair
+#ifndef AH_REM3_DIRECT_MAX
+#define AH_REM3_DIRECT_MAX 128
+#endif
+constexpr int REM3_DIRECT_MAX = AH_REM3_DIRECT_MAX;   // Remedy-3 lists up to this length are bisected by k_rem3_prep itself, one CTA per eigenpair
 constexpr int TILE_POLES = 2048; // inputs are padded to a multiple of this (a multiple of BTL)
 static_assert(TILE_POLES % BTL == 0, "tile size");
 static_assert((BS & (BS - 1)) == 0, "ring depth must be a power of two (stage = g & (BS-1); measured: BS = 3, 5, 6 cost 7 % in index arithmetic, BS = 2 and 4 perform alike)");
@@ -393,6 +396,7 @@ __device__ __forceinline__ void bisect_finalize(const Problem &P, const Outputs 
             }
         }
     }
+    if (go == GO_DONE && !interlace_ok(P.D, N, S.k, lambda)) go = GO_FULL;   // k_full repeats the reference's scheme and flags what it gets
     if (lane == 0) {
         const int64_t col = S.k - kbase;
         KState &G = ks[col];

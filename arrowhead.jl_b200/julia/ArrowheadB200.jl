@@ -59,7 +59,7 @@ function solve!(Λ::Vector{Float64}, U::Matrix{Float64}, κ::Vector{Info}, Ax::S
                     (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Int64, Int64, Ref{AhResult}),
                     ctx(), N, Ax.D, Ax.z, Ax.a, C_NULL, 1, n, r))
     end
-    any(s -> s & 0x0e != 0, status) && redo_on_host!(lam, Ublk, sind, kb, kz, knu, krho, qout, status, Ax)
+    any(s -> s & 0x2e != 0, status) && redo_on_host!(lam, Ublk, sind, kb, kz, knu, krho, qout, status, Ax)
     deflated && (U[zx, zx] = Ublk)                               # U[zx,zx[k]] = v for all k
     for k = 1:n
         Λ[zx[k]] = lam[k]
@@ -72,7 +72,7 @@ end
 # Julia per-k solver (arrowhead3.jl:419-550), exactly as before.
 function redo_on_host!(lam, Ublk, sind, kb, kz, knu, krho, qout, status, Ax)
     B = deepcopy(Ax)
-    for k in findall(s -> s & 0x0e != 0, status)
+    for k in findall(s -> s & 0x2e != 0, status)
         λ, v, info = Main.Arrowhead.eigen(Ax, B, k)
         lam[k] = λ; Ublk[:, k] = v
         sind[k] = info.Sind; kb[k] = info.Kb; kz[k] = info.Kz; knu[k] = info.Kν; krho[k] = info.Kρ; qout[k] = info.Qout

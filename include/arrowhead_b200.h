@@ -51,6 +51,9 @@ extern "C" {
 #define AH_ST_POLE_RETURN 4       /* Remedy 3 "came back with a pole" (arrowhead3.jl:474-496; raises in the reference) */
 #define AH_ST_REF_THROWS 8        /* the reference raises on this input (e.g. arrowhead4.jl:324) */
 #define AH_ST_ITER_LIMIT 16       /* Remedy-3 loop guard hit (the reference would keep looping) */
+#define AH_ST_INTERLACE 32        /* the computed value violates D_k <= lambda_k <= D_{k-1}: the reference's scheme lost all
+                                     accuracy here (first-stage K_nu ~ 1/eps, Remedy 3 re-shifted past the eigenvalue);
+                                     the reference returns such values silently -- redo this k in higher precision */
 
 /* where an eigenvector buffer lives */
 #define AH_MEM_HOST 0
