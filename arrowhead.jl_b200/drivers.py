@@ -125,8 +125,11 @@ def _deflate_duplicates(Ds, zs, zx, lam, rotation):
 
 # ---------------------------------------------------------------------------------------------------
 def eigen_symarrow(A: SymArrow, tau=None, *, ctx: Context | None = None, vectors="host", forward_tau=False,
-                   rotation="reference"):
-    """eigen(A::SymArrow, tau) -> (Eigen(values, vectors), Info).  vectors: "host" | "device" | None."""
+                   rotation="reference", out: np.ndarray | None = None):
+    """eigen(A::SymArrow, tau) -> (Eigen(values, vectors), Info).  vectors: "host" | "device" | None.
+    out: optional caller-owned Fortran-ordered n x n float64 array for the eigenvectors (pinned memory makes the
+    copy PCIe-fast: `Context.pinned_alloc`, torch `pin_memory`); when the input needs no deflation and no
+    permutation the column blocks are streamed into it while the next block is being computed."""
     ctx = ctx or get_context()
     D, z, a = A.D, A.z, A.a
     N = D.size
@@ -152,7 +155,9 @@ def eigen_symarrow(A: SymArrow, tau=None, *, ctx: Context | None = None, vectors
     zx = np.concatenate([zx, [n0 - 1]])
     keep, rots = _deflate_duplicates(Ds, zs, zx, lam, rotation)
     deflated = bool(z0.size or rots)
-    Udev = DeviceMatrix(ctx, n0, n0) if want else None
+    direct = (not deflated and out is not None and vectors == "host" and A.i == n0 and _is_identity(is_)
+              and out.shape == (n0, n0) and out.dtype == np.float64 and out.flags.f_contiguous)
+    Udev = DeviceMatrix(ctx, n0, n0) if (want and not direct) else None
     if deflated:
         rowmap = zx[np.concatenate([keep, [n - 1]])]
         if want:
@@ -165,13 +170,24 @@ def eigen_symarrow(A: SymArrow, tau=None, *, ctx: Context | None = None, vectors
             if want:
                 ctx.apply_givens_rows(Udev.ptr, Udev.ld, n0, i1, i2, c, s)
     else:
+        if direct:                         # ordered input: eigenvector blocks go straight into the caller's buffer
+            res = ctx.symarrow(Ds, zs, a, tau_k, vectors=False, U_host=out.ctypes.data, ldu=n0)
+            if _is_identity(jl_sortperm_desc(res.lam)):
+                info.scatter(np.arange(n0), res)
+                info.stats = res.stats
+                return Eigen(res.lam, out), info
+            Udev = DeviceMatrix(ctx, n0, n0)   # eigenvalues came out unsorted (never seen): take the general path
         res = ctx.symarrow(Ds, zs, a, tau_k, vectors=False, U_dev=Udev.ptr if want else None, ldu=n0)
         lam[:] = res.lam
         info.scatter(np.arange(n0), res)
     isi = np.argsort(is_, kind="stable")
     es = jl_sortperm_desc(lam)
     rows = np.concatenate([isi[: A.i - 1], [n0 - 1], isi[A.i - 1:]]).astype(np.int64)
-    E = Eigen(lam[es], _finish(ctx, Udev, rows, es, vectors))
+    Uout = _finish(ctx, Udev, rows, es, vectors)
+    if out is not None and isinstance(Uout, np.ndarray):
+        out[...] = Uout
+        Uout = out
+    E = Eigen(lam[es], Uout)
     out_info = info.permuted(es)
     out_info.stats = res.stats
     return E, out_info

@@ -529,3 +529,24 @@ def test_remedy3_direct_and_ring_paths_agree_bitwise(gpu_ctx):
         assert cols.size > 0
         assert torch.equal(Up[torch.as_tensor(cols - (k0 - 1), device="cuda")], U[torch.as_tensor(cols, device="cuda")])
         del Up
+
+
+def test_driver_streams_into_a_caller_buffer(gpu_ctx):
+    """eigen(SymArrow, out=...) with an ordered input: the eigenvector blocks are copied straight into the caller's
+    (pinned) buffer by the C-ABI call; with a permuted input the general path fills the same buffer."""
+    n = 600
+    D, z, a = gen_symarrow(n, seed=5)
+    ptr = gpu_ctx.pinned_alloc(n * n * 8)
+    try:
+        import ctypes
+        buf = np.ctypeslib.as_array((ctypes.c_double * (n * n)).from_address(ptr)).reshape((n, n), order="F")
+        E, info = ab.eigen(ab.SymArrow(D, z, a, n), ctx=gpu_ctx, out=buf)
+        assert E.vectors is buf
+        R, _ = ab.eigen(ab.SymArrow(D, z, a, n), ctx=gpu_ctx)
+        assert np.array_equal(R.vectors, buf) and np.array_equal(R.values, E.values)
+        p = np.random.default_rng(1).permutation(n - 1)
+        E2, _ = ab.eigen(ab.SymArrow(D[p], z[p], a, 7), ctx=gpu_ctx, out=buf)      # unsorted, arrow top inside
+        R2, _ = ab.eigen(ab.SymArrow(D[p], z[p], a, 7), ctx=gpu_ctx)
+        assert E2.vectors is buf and np.array_equal(R2.vectors, buf)
+    finally:
+        gpu_ctx.pinned_free(ptr)
