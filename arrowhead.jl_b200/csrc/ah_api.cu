@@ -272,7 +272,9 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     int64_t n_full = 0;
     int nbuf = 0, n_count_reads = 0;
     for (int q = 0; q < 64; ++q) ctx->hCounts[q] = 0;
-    const int nchunks = (int)((cnt + chunk - 1) / chunk);
+    // host-staged: a short first block gets the copy engine going early (the copies, not the kernels, bound this path)
+    const int64_t first = (staged && chunk < cnt) ? std::min<int64_t>(chunk, 1024) : chunk;
+    const int nchunks = (int)(1 + (cnt > first ? (cnt - first + chunk - 1) / chunk : 0));
     while ((int)ctx->chunk_ev.size() < 5 * nchunks) {
         cudaEvent_t e;
         AH_CUDA(cudaEventCreate(&e));
@@ -283,8 +285,8 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         AH_CUDA(cudaEventCreate(&e));
         ctx->side_ev.push_back(e);
     }
-    for (int64_t c0 = 0; c0 < cnt; c0 += chunk, ++nbuf) {
-        const int64_t cc = std::min(chunk, cnt - c0);
+    for (int64_t c0 = 0, cc = 0; c0 < cnt; c0 += cc, ++nbuf) {
+        cc = std::min(nbuf == 0 ? first : chunk, cnt - c0);
         const int slot = nbuf & 1;
         cudaEvent_t *E = &ctx->chunk_ev[5 * (size_t)nbuf];   // start | prep done | bisect done | vec done | full done
         Outputs Oc = O;
