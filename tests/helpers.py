@@ -78,6 +78,12 @@ def compare_range(gpu, orc, hi=None, *, lam_tol=10.0, vec_tol=100.0, k_tol=1e-9,
     # AH_ST_INTERLACE (32) is a diagnostic of this library only (the reference has no such test): eigenpairs it marks
     # are the ones where the reference's own answer is rounding noise, so they are excluded from the value comparison
     ok &= (gpu.status & 32) == 0
+    # ... and where the oracle itself returns NaN (e.g. sqrt of a rounding-negative mu + sigma^2 in arrowhead6.jl:420:
+    # the reference's value is NaN or 8 digits depending on which way the noise falls) the GPU must say so
+    ref_nan = np.isnan(orc.lam)
+    assert np.all(np.isnan(gpu.lam[ref_nan]) | ((gpu.status[ref_nan] & 32) != 0) | (gpu.krho[ref_nan] != 0)), \
+        "oracle NaN, GPU finite and unflagged"
+    ok &= ~ref_nan
     assert np.array_equal(gpu.qout[ok], orc.qout[ok]), "Qout differs"
     assert np.array_equal(gpu.status[ok], orc.status[ok]), "status differs"
     out = {"n_shift_ambiguous": int(bad.size), "n": int(cnt), "n_interlace_flagged": int(((gpu.status & 32) != 0).sum())}
@@ -86,7 +92,11 @@ def compare_range(gpu, orc, hi=None, *, lam_tol=10.0, vec_tol=100.0, k_tol=1e-9,
     den[den == 0] = 1.0
     lam_err = np.abs(gpu.lam - orc.lam) / den / EPS
     lam_noise = np.abs(hi.lam - orc.lam) / den / EPS if hi is not None else 0.0
-    lam_bar = lam_tol + 0.1 * knu + 3.0 * lam_noise
+    # (c) an inverse at a non-pole shift whose rho was accepted with K_rho >= 1e3 (HalfArrow's Remedies have no
+    #     double-double test for it) is determined to K_rho ulps only
+    with np.errstate(invalid="ignore"):
+        krho_w = np.where(orc.krho >= 1e3, np.minimum(orc.krho, 1.0 / EPS), 0.0)     # inf (P+Q == 0) counts as 1/eps
+    lam_bar = lam_tol + 0.1 * knu + 3.0 * lam_noise + krho_w
     out["lam_err_eps"] = float(lam_err[ok].max()) if ok.any() else 0.0
     out["lam_frac_within_10eps"] = float((lam_err[ok] <= lam_tol).mean()) if ok.any() else 1.0
     worst = int(np.argmax(np.where(ok, lam_err - lam_bar, -np.inf)))
@@ -104,8 +114,9 @@ def compare_range(gpu, orc, hi=None, *, lam_tol=10.0, vec_tol=100.0, k_tol=1e-9,
         if name in ("knu", "krho"):
             rem = orc.krho[ok][fin] != 0
             assert np.all(rel[~rem] <= k_tol), f"{name} differs: {rel[~rem].max():.3e}"
-            assert np.all(g[fin][rem] < 1e3 * (1 + 1e-9)) or np.all(g[fin][rem] <= o[fin][rem] * (1 + 1e-6)), \
-                f"{name} after Remedy 3 not accepted: {g[fin][rem].max():.3e}"
+            gr, orr = g[fin][rem], o[fin][rem]
+            accepted = (gr < 1e3 * (1 + 1e-9)) | ((orr >= 1e3) & (gr > orr / 1e3) & (gr < orr * 1e3))   # same regime
+            assert np.all(accepted), f"{name} after a Remedy not in the oracle's regime: {gr[~accepted]} vs {orr[~accepted]}"
         else:
             assert np.all(rel <= k_tol), f"{name} differs: {out[name + '_rel']:.3e}"
         assert np.array_equal(g[~fin], o[~fin]) or not (~fin).any()
@@ -130,7 +141,7 @@ def compare_range(gpu, orc, hi=None, *, lam_tol=10.0, vec_tol=100.0, k_tol=1e-9,
             out[vname + "_err_vs_hi_eps"] = float(hrel.max(axis=0)[ok].max()) if ok.any() else 0.0
         else:
             col_noise = 0.0
-        bar = vec_tol + knu + 3.0 * col_noise
+        bar = vec_tol + knu + 3.0 * col_noise + krho_w
         out[vname + "_err_eps"] = float(col_err[ok].max()) if ok.any() else 0.0
         out[vname + "_frac_within_100eps"] = float((col_err[ok] <= vec_tol).mean()) if ok.any() else 1.0
         worst = int(np.argmax(np.where(ok, col_err - bar, -np.inf)))
