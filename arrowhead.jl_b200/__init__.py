@@ -14,6 +14,7 @@ from ._lib import (LIB_PATH, ArrowheadError, Context, get_context, load_library,
                    ST_NU_INF, ST_NEEDS_BIGFLOAT, ST_POLE_RETURN, ST_REF_THROWS, ST_ITER_LIMIT, ST_INTERLACE)
 from .drivers import (DeviceMatrix, eigen, eigen_hermarrow, eigen_hermdpr1, eigen_symarrow, eigen_symdpr1, givens, jl_sortperm_desc,  # noqa: F401
                       svd, svd_halfarrow, tdc, tdc_device, tdc_recursive)
+from .roots import companion_arrow, rootsah  # noqa: F401
 from .sharding import k_partition, solve_sharded  # noqa: F401
 from .build import build_library  # noqa: F401
 

@@ -49,7 +49,7 @@ EXPORTS = [
     "ah_symarrow_eigen", "ah_symdpr1_eigen", "ah_halfarrow_svd",
     "ah_device_malloc", "ah_device_free", "ah_host_alloc_pinned", "ah_host_free_pinned",
     "ah_memcpy_d2h", "ah_memcpy_h2d", "ah_set_identity", "ah_apply_givens_rows", "ah_gather_permuted",
-    "ah_scale_rows_phase", "ah_symarrow_eigen_batched", "ah_gather_elements", "ah_gather_permuted_batched",
+    "ah_scale_rows_phase", "ah_symarrow_eigvals_dd", "ah_symarrow_eigen_batched", "ah_gather_elements", "ah_gather_permuted_batched",
     "ah_copy2d_batched", "ah_dgemm_batched",
     "ah_measure_fp64_peak", "ah_measure_store_bw",
 ]
@@ -91,6 +91,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ah_apply_givens_rows.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double]
     lib.ah_gather_permuted.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, _i64p, C.c_int64, _i64p, C.c_int64]
     u64p = C.POINTER(C.c_uint64)
+    lib.ah_symarrow_eigvals_dd.argtypes = [vp, C.c_int64, _dp, _dp, _dp, C.c_double, C.c_double, _dp, C.c_int64, C.c_int64,
+                                           C.POINTER(AhResult)]
     lib.ah_symarrow_eigen_batched.argtypes = [vp, C.c_int64, C.c_int64, _dp, _dp, _dp, _dp, C.POINTER(AhResult), C.c_int64]
     lib.ah_gather_elements.argtypes = [vp, vp, _i64p, C.c_int64, _dp]
     lib.ah_gather_permuted_batched.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int64, _i64p, C.c_int64,
@@ -235,6 +237,20 @@ class Context:
         args = (C.c_int64(nd), C.c_int64(nz), _ptr(D, _dp), _ptr(z, _dp), _ptr(tau_a, _dp))
         return self._run(self.lib.ah_halfarrow_svd, args, k0, k1, nz, nd + 1, vectors, U_dev, ldu, V_dev, ldv, rowmap_u,
                          rowmap_v, rowscale_v)
+
+    def symarrow_eigvals_dd(self, D, z, zlo, a, alo, tau, k0=1, k1=None):
+        """eigenvalues only, double-double border (z+zlo, a+alo): rootsah's per-k solver (arrowhead7.jl:351-495)"""
+        D = np.ascontiguousarray(D, np.float64); z = np.ascontiguousarray(z, np.float64); zlo = np.ascontiguousarray(zlo, np.float64)
+        tau_a = np.ascontiguousarray(tau, np.float64)
+        N = D.size
+        k1 = N + 1 if k1 is None else k1
+        res = RangeResult(k0, k1)
+        r = AhResult()
+        res.fill(r)
+        self._check(self.lib.ah_symarrow_eigvals_dd(self.handle, N, _ptr(D, _dp), _ptr(z, _dp), _ptr(zlo, _dp), float(a), float(alo),
+                                                    _ptr(tau_a, _dp), int(k0), int(k1), C.byref(r)))
+        res.stats = self.stats()
+        return res
 
     # ---- batched primitives (tdc) -----------------------------------------------------------------
     def symarrow_batched(self, D, z, a, tau=None, U_dev=None, ldu=0, ustride=0):

@@ -7,7 +7,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 SOURCES = [os.path.join(_PKG, "csrc", "ah_api.cu")]
-HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("ah_device.cuh", "ah_full.cuh", "ah_pipe.cuh")] + [
+HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("ah_device.cuh", "ah_full.cuh", "ah_pipe.cuh", "ah_roots.cuh")] + [
     os.path.join(os.path.dirname(_PKG), "include", "arrowhead_b200.h")]
 OUT = os.path.join(_PKG, "libarrowhead_b200.so")
 

@@ -20,6 +20,7 @@
 #include "ah_device.cuh"
 #include "ah_full.cuh"
 #include "ah_pipe.cuh"
+#include "ah_roots.cuh"
 
 namespace {
 
@@ -841,6 +842,69 @@ int ah_symarrow_eigen_batched(ah_ctx *ctx, int64_t nb, int64_t N, const double *
     if (N <= 64) k_full_batched<KIND_ARROW, 32><<<grid, 32, 0, st>>>(P, O, nb, av, mx, ustride);
     else if (N <= 512) k_full_batched<KIND_ARROW, 128><<<grid, 128, 0, st>>>(P, O, nb, av, mx, ustride);
     else k_full_batched<KIND_ARROW, 256><<<grid, 256, 0, st>>>(P, O, nb, av, mx, ustride);
+    AH_CUDA(cudaGetLastError());
+    AH_CUDA(cudaEventRecord(ctx->ev[1], st));
+    if ((rc = ensure_pinned(ctx, out_bytes(cnt)))) return rc;
+    AH_CUDA(cudaMemcpyAsync(ctx->hPinned, ctx->dOut.p, out_bytes(cnt), cudaMemcpyDeviceToHost, st));
+    AH_CUDA(cudaStreamSynchronize(st));
+    {
+        char *p = (char *)ctx->hPinned;
+        double *lam = carve<double>(p, cnt);
+        int64_t *sind = carve<int64_t>(p, cnt);
+        double *kb = carve<double>(p, cnt), *kz = carve<double>(p, cnt), *knu = carve<double>(p, cnt), *krho = carve<double>(p, cnt);
+        int64_t *qout = carve<int64_t>(p, cnt);
+        int32_t *steps = carve<int32_t>(p, cnt), *status = carve<int32_t>(p, cnt);
+        std::memcpy(out->lambda, lam, cnt * 8);
+        if (out->sind) std::memcpy(out->sind, sind, cnt * 8);
+        if (out->kb) std::memcpy(out->kb, kb, cnt * 8);
+        if (out->kz) std::memcpy(out->kz, kz, cnt * 8);
+        if (out->knu) std::memcpy(out->knu, knu, cnt * 8);
+        if (out->krho) std::memcpy(out->krho, krho, cnt * 8);
+        if (out->qout) std::memcpy(out->qout, qout, cnt * 8);
+        if (out->steps) std::memcpy(out->steps, steps, cnt * 4);
+        if (out->status) std::memcpy(out->status, status, cnt * 4);
+    }
+    float ms = 0.f;
+    AH_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->stats.kernel_ms = ms; ctx->stats.full_ms = ms; ctx->stats.launches = 1; ctx->stats.n_full = cnt;
+    ctx->stats.d2h_bytes = cnt * (8 * 7 + 4 * 2);
+    return AH_OK;
+}
+
+int ah_symarrow_eigvals_dd(ah_ctx *ctx, int64_t N, const double *D, const double *z_hi, const double *z_lo, double a_hi,
+                           double a_lo, const double *tau, int64_t k0, int64_t k1, ah_result *out) {
+    using namespace ah;
+    int rc = validate_common(ctx, N, D, z_hi, N, k0, k1, N + 1, out, false);
+    if (rc) return rc;
+    if (!z_lo || !tau) return fail(ctx, AH_ERR_INVALID_ARG, "z_lo and tau are required (rootsah passes [1e2,1e2,1e2,1e2,1e2])");
+    if (out->U || out->V) return fail(ctx, AH_ERR_INVALID_ARG, "eigenvalue-only entry point: U and V must be NULL");
+    if (!std::isfinite(a_hi) || !std::isfinite(a_lo)) return fail(ctx, AH_ERR_INVALID_ARG, "non-finite arrow top");
+    ctx->stats = ah_stats{};
+    AH_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t cnt = k1 - k0 + 1;
+    if ((rc = ensure(ctx, ctx->dD, N * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dW, N * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dW2, N * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dOut, out_bytes(cnt)))) return rc;
+    AH_CUDA(cudaMemcpyAsync(ctx->dD.p, D, N * 8, cudaMemcpyHostToDevice, st));
+    AH_CUDA(cudaMemcpyAsync(ctx->dW.p, z_hi, N * 8, cudaMemcpyHostToDevice, st));
+    AH_CUDA(cudaMemcpyAsync(ctx->dW2.p, z_lo, N * 8, cudaMemcpyHostToDevice, st));
+    ctx->stats.h2d_bytes = 3 * N * 8;
+    Problem P{};
+    P.N = N; P.D = (const double *)ctx->dD.p; P.w = (const double *)ctx->dW.p; P.a = a_hi;
+    for (int j = 0; j < 5; ++j) P.tau[j] = tau[j];
+    Outputs O{};
+    {
+        char *p = (char *)ctx->dOut.p;
+        O.lambda = carve<double>(p, cnt); O.sind = carve<int64_t>(p, cnt);
+        O.kb = carve<double>(p, cnt); O.kz = carve<double>(p, cnt); O.knu = carve<double>(p, cnt); O.krho = carve<double>(p, cnt);
+        O.qout = carve<int64_t>(p, cnt); O.steps = carve<int32_t>(p, cnt); O.status = carve<int32_t>(p, cnt);
+    }
+    AH_CUDA(cudaEventRecord(ctx->ev[0], st));
+    const int grid = (int)std::min<int64_t>(cnt, (int64_t)ctx->sm_count * 8);
+    if (N <= 512) k_roots<64><<<grid, 64, 0, st>>>(P, (const double *)ctx->dW2.p, a_lo, O, k0, cnt);
+    else k_roots<256><<<grid, 256, 0, st>>>(P, (const double *)ctx->dW2.p, a_lo, O, k0, cnt);
     AH_CUDA(cudaGetLastError());
     AH_CUDA(cudaEventRecord(ctx->ev[1], st));
     if ((rc = ensure_pinned(ctx, out_bytes(cnt)))) return rc;

@@ -148,6 +148,14 @@ int ah_apply_givens_rows(ah_ctx *ctx, double *U_dev, int64_t ld, int64_t ncols, 
 int ah_gather_permuted(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src,
                        const int64_t *rows, int64_t nrows, const int64_t *cols, int64_t ncols);
 
+/* rootsah (src/arrowhead7.jl:53-120): eigenvalues only of the arrowhead companion matrix whose border z and arrow top
+ * are known in double-double (z_hi+z_lo, a_hi+a_lo; built on the host, arrowhead7.jl:66-110).  Replaces the serial loop
+ * `for k=1:n; E[k],Qout[k] = eigen(A,zD,alphaD,k,tau); end` (:116-118) and the per-k solver :351-495 with one launch.
+ * Same input contract as ah_symarrow_eigen; tau is required (rootsah's default is [1e2,1e2,1e2,1e2,1e2]);
+ * out->U and out->V must be NULL. */
+int ah_symarrow_eigvals_dd(ah_ctx *ctx, int64_t N, const double *D, const double *z_hi, const double *z_lo, double a_hi,
+                           double a_lo, const double *tau, int64_t k0, int64_t k1, ah_result *out);
+
 /* ---- batched primitives for tdc() (src/arrowhead7.jl:10-36): one divide-and-conquer level = many independent
  * arrow merges of (nearly) equal size, then two back-transform GEMMs per merge ---------------------------------- */
 /* nb ordered irreducible SymArrow problems with the same number of poles N, solved in ONE launch by the complete

@@ -468,6 +468,191 @@ static void symarrow_k(int64_t N, const double *D, const double *z, double a, in
     *steps_out = steps; *status_out = status;
 }
 
+/* ------------------------------------------------------------------ rootsah: eigenvalue-only, double-double border */
+/* inv(A,zD,alphaD,i,tau) of arrowhead7.jl:132-225: as arrow_inv_shift_index, but the double-double recomputation of b
+ * uses the supplied double-double border zD = (z, zlo) and arrow top alphaD = (a, alo), there is a `Kb == Inf -> b = 0`
+ * branch and no BigFloat branch. */
+static void roots_inv_shift_index(int64_t N, const double *D, const double *z, const double *zlo, double a, double alo,
+                                  int64_t i, double tolb, double tolz, double *Bd, double *Bz, double *b_out,
+                                  double *Kb_out, double *Kz_out, int64_t *Qout) {
+    const int64_t ii = i - 1;
+    double wz = 1.0 / z[ii];
+    double sigma = D[ii];
+    for (int64_t k = 0; k < ii; ++k) { Bd[k] = 1.0 / (D[k] - sigma); Bz[k] = -z[k] * Bd[k] * wz; }
+    for (int64_t k = ii + 1; k < N; ++k) { Bd[k - 1] = 1.0 / (D[k] - sigma); Bz[k - 1] = -z[k] * Bd[k - 1] * wz; }
+    double as = a - sigma;
+    acc_t P = 0.0, Q = 0.0;
+    *Qout = 0;
+    for (int64_t k = 0; k < ii; ++k) { if (Bd[k] > 0.0) P += z[k] * z[k] * Bd[k]; else Q += z[k] * z[k] * Bd[k]; }
+    for (int64_t k = ii; k < N - 1; ++k) { if (Bd[k] > 0.0) P += z[k + 1] * z[k + 1] * Bd[k]; else Q += z[k + 1] * z[k + 1] * Bd[k]; }
+    if (as < 0) P -= as; else Q -= as;
+    double Kb = (P - Q) / fabs(P + Q);
+    double mz = fabs(z[0]);
+    for (int64_t k = 1; k < N; ++k) mz = jl_max(mz, fabs(z[k]));
+    double Kz = mz * fabs(wz);
+    double b;
+    if (Kb < tolb || Kz < tolz) {
+        b = (P + Q) * wz * wz;
+    } else if (isinf(Kb)) {
+        b = 0.0;
+    } else {
+        *Qout = 1;
+        dd s1 = dd_from(sigma);
+        dd wzd = {z[ii], zlo[ii]};
+        dd aD = {a, alo};
+        dd ad = dd_sub(aD, s1);
+        dd Pd = dd_from(0.0), Qd = dd_from(0.0);
+        for (int64_t k = 0; k < N; ++k) {
+            if (k == ii) continue;
+            dd Dd = dd_sub(dd_from(D[k]), s1);
+            dd zk = {z[k], zlo[k]};
+            dd t = dd_div(dd_mul(zk, zk), Dd);
+            if (Dd.hi > 0.0) Pd = dd_add(Pd, t); else Qd = dd_add(Qd, t);
+        }
+        if (ad.hi < 0) Pd = dd_sub(Pd, ad); else Qd = dd_sub(Qd, ad);
+        dd bd = dd_div(dd_add(Pd, Qd), dd_mul(wzd, wzd));
+        b = dd_to_double(bd);
+    }
+    Bd[N - 1] = 0.0;
+    Bz[N - 1] = wz;
+    *b_out = b; *Kb_out = Kb; *Kz_out = Kz;
+}
+
+/* inv(A,zD,alphaD,sigma::Float64,tau) of arrowhead7.jl:232-292 */
+static void roots_inv_shift_value(int64_t N, const double *D, const double *z, const double *zlo, double a, double alo,
+                                  double sigma, double tol, double *D1, double *u1, double *rho_out, double *Krho_out,
+                                  int64_t *Qout) {
+    for (int64_t k = 0; k < N; ++k) { D1[k] = 1.0 / (D[k] - sigma); u1[k] = z[k] * D1[k]; }
+    D1[N] = 0.0;
+    u1[N] = -1.0;
+    double as = a - sigma;
+    acc_t P = 0.0, Q = 0.0;
+    *Qout = 0;
+    for (int64_t k = 0; k < N; ++k) { if (D1[k] > 0.0) P += z[k] * z[k] * D1[k]; else Q += z[k] * z[k] * D1[k]; }
+    if (as < 0) P -= as; else Q -= as;
+    double Krho = (P - Q) / fabs(P + Q);
+    double rho;
+    if (Krho < tol) {
+        rho = -1.0 / (P + Q);
+    } else {
+        *Qout = 1;
+        dd Pd = dd_from(0.0), Qd = dd_from(0.0);
+        dd s1 = dd_from(sigma);
+        dd aD = {a, alo};
+        dd ad = dd_sub(aD, s1);
+        for (int64_t k = 0; k < N; ++k) {
+            dd zk = {z[k], zlo[k]};
+            dd t = dd_div(dd_mul(zk, zk), dd_sub(dd_from(D[k]), s1));
+            if (D1[k] > 0.0) Pd = dd_add(Pd, t); else Qd = dd_add(Qd, t);
+        }
+        if (ad.hi + ad.lo < 0) Pd = dd_sub(Pd, ad); else Qd = dd_sub(Qd, ad);
+        dd r = dd_div(dd_from(1.0), dd_add(Pd, Qd));
+        rho = -(r.hi + r.lo);
+    }
+    *rho_out = rho; *Krho_out = Krho;
+}
+
+/* eigen(A,zD,alphaD,k,tau) of arrowhead7.jl:351-495: k-th eigenvalue only.  status: AH_ST_POLE_RETURN where the
+ * reference raises (:436 `map(Double,A.D)-sigma_v`), AH_ST_REF_THROWS for the unguarded A.D[i-1] with i == 1 (:474). */
+static void rootsah_k(int64_t N, const double *D, const double *z, const double *zlo, double a, double alo, int64_t k,
+                      const double *tau, scratch_t *s, double *lambda_out, int64_t *sind, double *kb, double *kz,
+                      double *knu, double *krho, int64_t *qout, int32_t *steps_out, int32_t *status_out) {
+    const int64_t n = N + 1;
+    double Kb = 0, Kz = 0, Knu = 0, Krho = 0;
+    int64_t Qout = 0;
+    int32_t steps = 0, status = 0;
+    double sigma, lambda;
+    int64_t i;
+    char side;
+    if (k == 1) { sigma = D[0]; i = 1; side = 'R'; }
+    else if (k == n) { sigma = D[N - 1]; i = N; side = 'L'; }
+    else {   /* shift selection in double-double (:381-389) */
+        dd Dk = dd_from(D[k - 1]);
+        dd middle = dd_div(dd_sub(dd_from(D[k - 2]), Dk), dd_from(2.0));
+        dd F = dd_from(0.0);
+        for (int64_t l = 0; l < N; ++l) {
+            dd zl = {z[l], zlo[l]};
+            F = dd_add(F, dd_div(dd_mul(zl, zl), dd_sub(dd_sub(dd_from(D[l]), Dk), middle)));
+        }
+        dd aD = {a, alo};
+        F = dd_sub(dd_sub(dd_sub(aD, Dk), middle), F);
+        if (F.hi + F.lo < 0.0) { sigma = D[k - 1]; i = k; side = 'R'; }
+        else { sigma = D[k - 2]; i = k - 1; side = 'L'; }
+    }
+    double b;
+    roots_inv_shift_index(N, D, z, zlo, a, alo, i, tau[0], tau[1], s->bd, s->bz, &b, &Kb, &Kz, &Qout);
+    double nu = bisect_arrow(s->bd, s->bz, b, N, side, s->w, &steps);
+    if (isinf(nu)) {
+        lambda = sigma;
+        status |= AH_ST_NU_INF;
+    } else {
+        double nu1 = 0.0;
+        for (int64_t l = 0; l < N; ++l) nu1 = jl_max(nu1, fabs(s->bd[l]) + fabs(s->bz[l]));
+        for (int64_t l = 0; l < N; ++l) s->t[l] = fabs(s->bz[l]);
+        nu1 = jl_max(jl_pairwise_sum(s->t, 0, N - 1) + fabs(b), nu1);
+        Knu = nu1 / fabs(nu);
+        double sig_v = sigma, mu;
+        if (Knu < tau[2]) {
+            mu = 1.0 / nu;
+            lambda = mu + sigma;
+        } else {   /* Remedy 3, once (:415-459); nu keeps its first-stage value for the Remedy-1 test below */
+            nu = side == 'R' ? fabs(nu) : -fabs(nu);
+            nu1 = -jl_sign(nu) * nu1;
+            double sigma1 = (nu1 + nu) / (2.0 * nu * nu1) + sigma;
+            int pole = 0;
+            for (int64_t l = 0; l < N; ++l) if (jl_isequal(sigma1, D[l])) { pole = 1; break; }
+            if (pole) {
+                status |= AH_ST_POLE_RETURN;
+                mu = 1.0 / nu;
+                lambda = mu + sigma;
+            } else {
+                int64_t Qout1 = 0;
+                double rho;
+                roots_inv_shift_value(N, D, z, zlo, a, alo, sigma1, tau[3], s->d1, s->u1, &rho, &Krho, &Qout1);
+                double nub = bisect_dpr1(s->d1, s->u1, rho, N + 1, side, s->w, &steps);
+                mu = 1.0 / nub;
+                sig_v = sigma1;
+                lambda = mu + sigma1;
+            }
+            if (Qout == 1) Qout = Qout + 2;
+        }
+        /* Remedy 1 (:464-487); the inverse at 0 is the generic inv(A,0.0,tau) of arrowhead3.jl (plain z) */
+        if ((fabs(D[i - 1]) + fabs(1.0 / nu)) / fabs(lambda) > tau[4]) {
+            int c1 = (k == 1 && D[0] < 0.0);
+            int c2 = (k == n && D[N - 1] > 0.0);
+            int c3 = (i < n - 1 && side == 'L' && jl_sign(D[i - 1]) + jl_sign(D[i]) == 0);
+            int c4 = 0;
+            if (!(c1 || c2 || c3) && side == 'R') {
+                if (i == 1) status |= AH_ST_REF_THROWS;      /* A.D[0]: BoundsError in the reference */
+                else c4 = (jl_sign(D[i - 1]) + jl_sign(D[i - 2]) == 0);
+            }
+            if (c1 || c2 || c3 || c4) {
+                int64_t Qout1 = 0;
+                double rho;
+                arrow_inv_shift_value(N, D, z, a, 0.0, tau[3], s->d1, s->u1, &rho, &Krho, &Qout1, &status);
+                if (Qout == 1) Qout = Qout + 4;
+                if (isinf(rho)) {
+                    lambda = 0.0;
+                } else {
+                    /* v = normalize([z./((D-sig_v)-mu); -1]) */
+                    double *v = s->t;
+                    acc_t ss = 0.0;
+                    for (int64_t l = 0; l < N; ++l) { v[l] = z[l] / ((D[l] - sig_v) - mu); ss += v[l] * v[l]; }
+                    v[N] = -1.0; ss += 1.0;
+                    double inrm = 1.0 / sqrt(ss);
+                    acc_t s1 = 0.0, s2 = 0.0;
+                    for (int64_t l = 0; l < n; ++l) { double vl = v[l] * inrm; s1 += vl * vl * s->d1[l]; s2 += vl * s->u1[l]; }
+                    double nu1r = s1 + rho * (s2 * s2);
+                    lambda = 1.0 / nu1r;
+                }
+            }
+        }
+    }
+    *lambda_out = lambda;
+    *sind = i; *kb = Kb; *kz = Kz; *knu = Knu; *krho = Krho; *qout = Qout;
+    *steps_out = steps; *status_out = status;
+}
+
 /* ------------------------------------------------------------------ SymDPR1 */
 /* inv!(B,A::SymDPR1,i,tau): B gets n-1 entries, no slot. */
 static void dpr1_inv_shift_index(int64_t n, const double *D, const double *u, double r, int64_t i,
@@ -986,6 +1171,36 @@ int ah_oracle_halfarrow_svd(int64_t nd, int64_t nz, const double *D, const doubl
         }
         if (ok) scratch_free(&s);
         free(uloc); free(vloc);
+    }
+    return err;
+}
+
+/* rootsah's loop `for k=1:n; E[k],Qout[k] = eigen(A,zD,alphaD,k,tau); end` (arrowhead7.jl:116-118; serial in the reference) */
+int ah_oracle_rootsah_eigvals(int64_t N, const double *D, const double *z, const double *zlo, double a, double alo,
+                              const double *tau, int64_t k0, int64_t k1, int nthreads, double *lambda, int64_t *sind,
+                              double *kb, double *kz, double *knu, double *krho, int64_t *qout, int32_t *steps,
+                              int32_t *status) {
+    if (N < 1 || k0 < 1 || k1 > N + 1 || k1 < k0) return -1;
+    int err = 0;
+    if (nthreads < 1) nthreads = ah_oracle_max_threads();
+#pragma omp parallel num_threads(nthreads)
+    {
+        scratch_t s;
+        int ok = scratch_alloc(&s, N + 1);
+        if (!ok) {
+#pragma omp atomic write
+            err = -2;
+        }
+#pragma omp barrier
+        if (!err) {
+#pragma omp for schedule(static)
+            for (int64_t k = k0; k <= k1; ++k) {
+                int64_t c = k - k0;
+                rootsah_k(N, D, z, zlo, a, alo, k, tau, &s, &lambda[c], &sind[c], &kb[c], &kz[c], &knu[c], &krho[c],
+                          &qout[c], &steps[c], &status[c]);
+            }
+        }
+        if (ok) scratch_free(&s);
     }
     return err;
 }

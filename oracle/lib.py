@@ -80,6 +80,9 @@ class OracleLib:
         self.lib.ah_oracle_halfarrow_svd.argtypes = [
             C.c_int64, C.c_int64, _dp, _dp, _dp, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int64,
             _dp, C.c_int64, *common_tail]
+        self.lib.ah_oracle_rootsah_eigvals.restype = C.c_int
+        self.lib.ah_oracle_rootsah_eigvals.argtypes = [
+            C.c_int64, _dp, _dp, _dp, C.c_double, C.c_double, _dp, C.c_int64, C.c_int64, C.c_int, _dp, *common_tail]
         self.lib.ah_oracle_dd_op.restype = None
         self.lib.ah_oracle_dd_op.argtypes = [C.c_int, _dp, _dp, _dp]
         self.lib.ah_oracle_max_threads.restype = C.c_int
@@ -112,6 +115,21 @@ class OracleLib:
         if rc != 0:
             raise RuntimeError(f"ah_oracle_symarrow_eigen rc={rc}")
         return RangeResult(k0, k1, lam, U, None, *info)
+
+    def rootsah_eigvals(self, D, z, zlo, a, alo, tau, k0=1, k1=None, nthreads=0) -> RangeResult:
+        """eigen(A,zD,alphaD,k,tau) for k0..k1 (arrowhead7.jl:351-495): eigenvalues + Qout of the companion arrow"""
+        D = np.ascontiguousarray(D, np.float64); z = np.ascontiguousarray(z, np.float64); zlo = np.ascontiguousarray(zlo, np.float64)
+        tau = np.ascontiguousarray(tau, np.float64)
+        N = D.size
+        k1 = N + 1 if k1 is None else k1
+        cnt = k1 - k0 + 1
+        lam = np.zeros(cnt)
+        info = self._info(cnt)
+        rc = self.lib.ah_oracle_rootsah_eigvals(N, _p(D, _dp), _p(z, _dp), _p(zlo, _dp), float(a), float(alo), _p(tau, _dp),
+                                                k0, k1, nthreads, _p(lam, _dp), *self._info_ptrs(info))
+        if rc != 0:
+            raise RuntimeError(f"ah_oracle_rootsah_eigvals rc={rc}")
+        return RangeResult(k0, k1, lam, None, None, *info)
 
     def symdpr1(self, D, u, rho, tau, k0=1, k1=None, vectors=True, nthreads=0) -> RangeResult:
         D = np.ascontiguousarray(D, np.float64); u = np.ascontiguousarray(u, np.float64)
