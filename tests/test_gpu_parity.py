@@ -311,6 +311,15 @@ def test_config1_n32768_properties(gpu_ctx, oracle_lib, oracle_hi):
     assert np.all(np.diff(G.lam) < 0)                                    # strictly descending, interlacing
     assert np.all(G.lam[1:] < D) and np.all(G.lam[:-1] > D)
     assert abs(G.lam.sum() - (D.sum() + a)) <= 20 * n * EPS * np.abs(G.lam).sum() / n * 10   # trace
+    # every eigenvalue and every Info record against the oracle (vectors off: 5 s on the box's host cores)
+    Oall = oracle_lib.symarrow(D, z, a, _tau(n - 1), vectors=False)
+    Hall = oracle_hi.symarrow(D, z, a, _tau(n - 1), vectors=False)
+    from types import SimpleNamespace
+    full = compare_range(SimpleNamespace(k0=1, lam=G.lam, sind=G.sind, qout=G.qout, status=G.status, kb=G.kb, kz=G.kz, knu=G.knu,
+                                         krho=G.krho, U=None, V=None), Oall, Hall, k_tol=1e-7,
+                         margin_fn=lambda kk: shift_margin_symarrow(D, z, a, kk))
+    assert full["lam_frac_within_10eps"] > 0.999, full
+    assert np.array_equal(G.krho != 0, Oall.krho != 0)                   # the same eigenpairs took Remedy 3
     rng = np.random.default_rng(0)
     sample = np.unique(np.concatenate([[1, 2, n - 1, n], rng.integers(1, n + 1, 24), np.flatnonzero(G.steps > 80)[:8] + 1]))
     from types import SimpleNamespace
