@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -36,6 +37,9 @@ struct DevBuf {
 struct ah_ctx {
     int device = 0;
     int sm_count = 0;
+    int quantum = -1;           // k_bisect time slice (steps): < 0 automatic, 0 off (tuning knob ARROWHEAD_B200_QUANTUM)
+    int window = 2;             // time slicing starts when fewer than window x slots eigenpairs wait (ARROWHEAD_B200_WINDOW)
+    unsigned bisect_tag = 0;    // per-launch tag of the requeue FIFO entries
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;   // high priority: the short Remedy-3 round runs beside k_vec
@@ -47,7 +51,7 @@ struct ah_ctx {
     std::string err;
     int mode = 0;
     ah_stats stats = {};
-    DevBuf dD, dW, dW2, dKs, dRList, dZ, dMap1, dMap2, dScale, dOut, dList, dCount, dStage[2];
+    DevBuf dD, dW, dW2, dKs, dRList, dZ, dMap1, dMap2, dScale, dOut, dList, dCount, dQueue, dStage[2];
     void *hPinned = nullptr;  // pinned bounce buffer for the per-k outputs
     size_t hPinnedCap = 0;
     std::vector<double> hPadD, hPadW, hPadW2;
@@ -252,6 +256,14 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     if ((rc = ensure(ctx, ctx->dKs, (size_t)cnt * sizeof(ah::KState)))) return rc;
     if ((rc = ensure(ctx, ctx->dRList, cnt * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dCount, 256))) return rc;
+    {   // requeue FIFO of k_bisect's time slicing; entries carry a per-launch tag, so it is cleared only when (re)allocated
+        const size_t qbytes = ah::bisect_queue_entries(cnt) * 8;
+        if (qbytes > ctx->dQueue.cap) {
+            if ((rc = ensure(ctx, ctx->dQueue, qbytes))) return rc;
+            AH_CUDA(cudaMemsetAsync(ctx->dQueue.p, 0, ctx->dQueue.cap, st));
+            ctx->bisect_tag = 0;
+        }
+    }
 
     // ---- eigenvector destination: device-resident, or host through a double-buffered staging area
     const bool wantU = out->U != nullptr, wantV = (L.kind == KIND_HALF) && out->V != nullptr;
@@ -312,11 +324,16 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         if (ctx->mode == 0) {
             KState *ks = (KState *)ctx->dKs.p;
             int64_t *rlist = (int64_t *)ctx->dRList.p;
-            AH_CUDA(cudaMemsetAsync(dcount, 0, 32, st));
+            AH_CUDA(cudaMemsetAsync(dcount, 0, 64, st));
             rc = ah::launch_prep(L.kind, P, ks, kb, cc, dlist, dcount, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_prep launch");
             AH_CUDA(cudaEventRecord(E[1], st));
-            rc = ah::launch_bisect(L.kind, 0, P, Oc, ks, kb, cc, dlist, rlist, dcount, ctx->sm_count, st);
+            if (++ctx->bisect_tag == 0) {   // tags wrapped: forget the old entries
+                AH_CUDA(cudaMemsetAsync(ctx->dQueue.p, 0, ctx->dQueue.cap, st));
+                ctx->bisect_tag = 1;
+            }
+            rc = ah::launch_bisect(L.kind, 0, P, Oc, ks, kb, cc, dlist, rlist, dcount, (unsigned long long *)ctx->dQueue.p,
+                                   (long long)(ctx->dQueue.cap / 8), ctx->bisect_tag, ctx->quantum, ctx->window, ctx->sm_count, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect launch");
             AH_CUDA(cudaEventRecord(E[2], st));
             // Remedy 3 on the fast path: re-shift (k_rem3_prep) and bisect again (round 1) for the ~1 % of eigenpairs
@@ -335,7 +352,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                 AH_CUDA(cudaEventRecord(SE[0], rs));
                 rc = ah::launch_rem3_prep(L.kind, P, Oc, ks, kb, guess, rlist, dlist, dcount, ctx->sm_count, rs);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_rem3_prep launch");
-                rc = ah::launch_bisect(L.kind, 1, P, Oc, ks, kb, guess, dlist, rlist, dcount, ctx->sm_count, rs);
+                rc = ah::launch_bisect(L.kind, 1, P, Oc, ks, kb, guess, dlist, rlist, dcount, nullptr, 0, 0u, 0, 0, ctx->sm_count, rs);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect round 1 launch");
                 AH_CUDA(cudaEventRecord(SE[1], rs));
                 ctx->stats.launches += 2;
@@ -592,6 +609,8 @@ int ah_create(ah_ctx **pctx, int device) {
     if (!ctx) return fail(nullptr, AH_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *q = getenv("ARROWHEAD_B200_QUANTUM")) ctx->quantum = atoi(q);
+    if (const char *q = getenv("ARROWHEAD_B200_WINDOW")) ctx->window = std::max(1, atoi(q));
     if ((e = cudaSetDevice(device)) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaSetDevice"); }
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -620,7 +639,7 @@ void ah_destroy(ah_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (DevBuf *b : {&ctx->dD, &ctx->dW, &ctx->dW2, &ctx->dKs, &ctx->dRList, &ctx->dZ, &ctx->dMap1, &ctx->dMap2, &ctx->dScale, &ctx->dOut, &ctx->dList,
-                      &ctx->dCount, &ctx->dStage[0], &ctx->dStage[1]})
+                      &ctx->dCount, &ctx->dQueue, &ctx->dStage[0], &ctx->dStage[1]})
         if (b->p) cudaFree(b->p);
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     if (ctx->hCounts) cudaFreeHost(ctx->hCounts);

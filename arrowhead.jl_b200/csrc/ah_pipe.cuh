@@ -37,8 +37,9 @@
 namespace ah {
 
 enum : int { KS_READY = 0, KS_HANDOFF = 1, KS_DONE = 2, KS_REM3 = 3, KS_REM3_READY = 4, KS_DONE1 = 5 };   // DONE1: finished in round 1
-// counters (unsigned long long[4]): [0] hand-over list length, [1] k_bisect round-0 work counter,
-//                                   [2] Remedy-3 list length,   [3] k_bisect round-1 work counter
+// counters (unsigned long long[8]): [0] hand-over list length, [1] k_bisect round-0 ticket counter,
+//                                   [2] Remedy-3 list length,   [3] k_bisect round-1 ticket counter,
+//                                   [4] round-0 requeue count,  [5] round-0 eigenpairs finished
 
 struct KState {   // 128 bytes per eigenpair
     double sigma, wz, b, left, right, nu1, Kb, Kz;   // written by k_prep
@@ -309,11 +310,12 @@ constexpr int TILE_POLES = 2048; // inputs are padded to a multiple of this (a m
 static_assert(TILE_POLES % BTL == 0, "tile size");
 static_assert((BS & (BS - 1)) == 0, "ring depth must be a power of two (stage = g & (BS-1); measured: BS = 3, 5, 6 cost 7 % in index arithmetic, BS = 2 and 4 perform alike)");
 
-enum : int { PH_FREE = 0, PH_BISECT, PH_DONE };
+enum : int { PH_FREE = 0, PH_BISECT, PH_DONE, PH_PENDING };
 
 struct BSlot {   // cold per-slot state, touched by warp j only
     int64_t k, i;
-    int phase, sideR, steps, pad_;
+    int phase, sideR, steps, q;   // q: steps since the slot took this eigenpair (time slice)
+    unsigned long long ticket;    // PH_PENDING: the work ticket this slot is waiting on
     double sigma, wz2, b, left, right, m, nu1, Kb, Kz;
     double knu0, krho, sig2;   // round 1: first K_nu (HalfArrow keeps it), K_rho, squared shift (HalfArrow)
 };
@@ -325,7 +327,7 @@ struct BisectShared {
     alignas(16) double2 hot[BJ];   // (sigma, m) of every slot for the coming sweep
     double part[BJ][BW];
     long long skip[BJ];            // 0-based index of the slot's shift pole, -1: none (idle slot, or Remedy-3 round)
-    int act[BJ];                   // slot is bisecting in the coming sweep
+    int act[BJ];                   // coming sweep: 1 slot is bisecting, 2 slot waits for its ticket, 0 slot has retired
     double save[BJ];               // accumulator of slot j saved by the one thread that owns its shift pole
     BSlot slot[BJ];
 };
@@ -424,10 +426,31 @@ __device__ __forceinline__ bool bisect_converged(const BSlot &S) {
     return !((S.right - S.left) > 2.0 * kEps * fmax(fabs(S.left), fabs(S.right)));
 }
 
+__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+// Work distribution.  Eigenpairs are handed to slots by ticket: ticket t < cnt is eigenpair t of the block (round 1:
+// entry t of the Remedy-3 list), taken with one atomicAdd.  A bisection is ~55 dependent sweeps, so with plain
+// first-come-first-served the last "wave" of a launch leaves slots idle: half a wave at the end of a long launch, and
+// most of a wave when the k-range is short (a 1/8 shard of n = 32768 is 1.7 eigenpairs per slot: 2 x 55 sweeps with
+// 27 % of the slots idle in the second half).  Round 0 therefore TIME-SLICES once the eigenpairs that are still
+// waiting would fit in two more waves: a slot that has spent `quantum` steps on its eigenpair while others wait
+// writes the bracket back to its KState record, appends the eigenpair to a FIFO (ticket cnt + r, r = dcount[4]++;
+// entry = launch tag << 32 | column, so the buffer never needs clearing) and takes the next ticket.  All eigenpairs
+// in flight then advance at the same rate and finish together: the launch ends after ~(sum of steps) / slots sweeps.
+// A slot whose ticket has no entry yet idles (PH_PENDING; it never blocks its CTA) until the entry appears or every
+// eigenpair of the block is finished (dcount[5] == cnt).  Which slot advances an eigenpair, and when, has no
+// influence on its arithmetic: results are bitwise independent of the schedule.
+// NSLOT: slots per CTA.  All NSLOT slots are evaluated in every sweep (skipping idle ones with a branch breaks the
+// interleaving of the chains and costs more than it saves), so a block of fewer than 8 eigenpairs per CTA runs with
+// 7 or 6 slots.  Round 1 is the exception: its list is ~1 % of the block, slot j of a CTA is used only while
+// j * CTAs < cnt (which spreads the list over all CTAs) and the sweep skips the unused slots.
 template <int KIND, int ROUND, int NSLOT>
 __global__ void __launch_bounds__(BT, BCTAS)
 k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *__restrict__ dlist,
-         int64_t *__restrict__ rlist, unsigned long long *dcount) {
+         int64_t *__restrict__ rlist, unsigned long long *dcount, unsigned long long *__restrict__ queue, long long qcap,
+         unsigned tag, int quantum, int window) {
     static_assert(NSLOT >= 1 && NSLOT <= BJ && NSLOT <= BW, "one warp per slot");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BisectShared &sh = *reinterpret_cast<BisectShared *>(smem_raw);
@@ -439,9 +462,12 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < NSLOT) { sh.slot[tid].phase = PH_FREE; sh.skip[tid] = -1; sh.act[tid] = 0; sh.hot[tid] = make_double2(0.0, 0.0); }
-    if (ROUND == 1) cnt = (int64_t)dcount[2];   // round 1 works through the Remedy-3 list
+    if (ROUND == 1) { cnt = (int64_t)dcount[2]; quantum = 0; }   // round 1 works through the (short) Remedy-3 list
     __syncthreads();
     if (ROUND == 1 && cnt <= REM3_DIRECT_MAX) return;   // short list: k_rem3_prep has bisected it directly
+    const unsigned long long ucnt = (unsigned long long)cnt;
+    const unsigned long long slots_total = (unsigned long long)gridDim.x * NSLOT;
+    unsigned long long *const tickets = dcount + (ROUND == 0 ? 1 : 3);
 
     bool wrapped = false;    // g_issue has wrapped around 2^32 at least once
     uint32_t g_issue = 0;    // tiles issued (thread 0 only); wraps mod 2^32, a multiple of 2*BS -> parities stay consistent
@@ -488,46 +514,93 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                     if (goleft) S.left = m; else S.right = m;
                     S.m = (S.left + S.right) / 2.0;
                     S.steps += 1;
+                    S.q += 1;
                 }
                 __syncwarp();
             }
-            // converged (the reference tests before the first step, too) -> finalise, then fetch new work
             while (true) {
                 if (S.phase == PH_BISECT) {
-                    if (!bisect_converged(S)) break;
-                    bisect_finalize<KIND, ROUND>(P, O, ks, S, kbase, dlist, rlist, dcount, lane);
-                    __syncwarp();
-                    if (lane == 0) S.phase = PH_FREE;
-                    __syncwarp();
+                    if (bisect_converged(S)) {   // (the reference tests before the first step, too) -> finalise
+                        bisect_finalize<KIND, ROUND>(P, O, ks, S, kbase, dlist, rlist, dcount, lane);
+                        __syncwarp();
+                        if (lane == 0) { if (quantum > 0) atomicAdd(dcount + 5, 1ull); S.phase = PH_FREE; }
+                        __syncwarp();
+                    } else {
+                        // time slice used up and others are waiting -> back of the queue
+                        int swap = 0;
+                        const int qv = S.q;
+                        __syncwarp();
+                        if (ROUND == 0 && quantum > 0 && qv >= quantum) {
+                            if (lane == 0) {
+                                const unsigned long long head = ld_volatile(tickets), nreq = ld_volatile(dcount + 4);
+                                const unsigned long long tail = ucnt + nreq;
+                                swap = (head < tail && tail - head < (unsigned long long)window * slots_total &&
+                                        nreq + slots_total < (unsigned long long)qcap) ? 1 : 0;
+                                S.q = 0;
+                            }
+                            swap = __shfl_sync(0xffffffffu, swap, 0);
+                        }
+                        if (!swap) break;
+                        if (lane == 0) {
+                            KState &G = ks[S.k - kbase];
+                            G.left = S.left; G.right = S.right; G.steps = S.steps;
+                            __threadfence();
+                            const unsigned long long r = atomicAdd(dcount + 4, 1ull);
+                            *reinterpret_cast<volatile unsigned long long *>(queue + r) =
+                                ((unsigned long long)tag << 32) | (unsigned long long)(uint32_t)(S.k - kbase);
+                            S.phase = PH_FREE;
+                        }
+                        __syncwarp();
+                    }
                 }
                 if (S.phase == PH_DONE) break;
-                if (ROUND == 1 && (int64_t)warp * gridDim.x >= cnt) {   // spread the short list over all CTAs
+                if (ROUND == 1 && (int64_t)warp * gridDim.x >= cnt) {   // spread a short list over all CTAs
                     __syncwarp();
                     if (lane == 0) S.phase = PH_DONE;
                     __syncwarp();
                     break;
                 }
-                // PH_FREE: next eigenpair that k_prep (round 1: k_rem3_prep) left ready
-                unsigned long long wi = 0;
-                if (lane == 0) wi = atomicAdd(dcount + (ROUND == 0 ? 1 : 3), 1ull);
-                wi = __shfl_sync(0xffffffffu, wi, 0);
-                if ((int64_t)wi >= cnt) {
+                if (S.phase == PH_FREE) {
+                    if (lane == 0) { S.ticket = atomicAdd(tickets, 1ull); S.phase = PH_PENDING; }
                     __syncwarp();
-                    if (lane == 0) S.phase = PH_DONE;
+                }
+                // PH_PENDING: which eigenpair does the ticket stand for?
+                long long col = -1;      // >= 0: column of the block, -1: not there yet, -2: never
+                if (lane == 0) {
+                    const unsigned long long t = S.ticket;
+                    if (t < ucnt) col = (ROUND == 0) ? (long long)t : (long long)(rlist[t] - kbase);
+                    else if (quantum == 0) col = -2;
+                    else {
+                        const unsigned long long r = t - ucnt;
+                        const unsigned long long e = (r < (unsigned long long)qcap) ? ld_volatile(queue + r) : 0ull;
+                        if ((unsigned)(e >> 32) == tag) { __threadfence(); col = (long long)(uint32_t)e; }
+                        else if (ld_volatile(dcount + 5) >= ucnt) col = -2;   // everything is finished: nothing will be queued any more
+                    }
+                }
+                col = __shfl_sync(0xffffffffu, col, 0);
+                if (col < 0) {
+                    __syncwarp();
+                    if (lane == 0 && col == -2) S.phase = PH_DONE;
                     __syncwarp();
                     break;
                 }
-                const int64_t knew = (ROUND == 0) ? kbase + (int64_t)wi : rlist[wi];
-                const KState &G = ks[knew - kbase];
-                if (G.flag != (ROUND == 0 ? KS_READY : KS_REM3_READY)) continue;
+                const KState &G = ks[col];
+                if (G.flag != (ROUND == 0 ? KS_READY : KS_REM3_READY)) {   // k_prep handed it over: not for this kernel
+                    __syncwarp();
+                    if (lane == 0) { if (quantum > 0) atomicAdd(dcount + 5, 1ull); S.phase = PH_FREE; }
+                    __syncwarp();
+                    continue;
+                }
                 __syncwarp();
                 if (lane == 0) {
-                    S.k = knew; S.i = G.i; S.sideR = G.sideR;
+                    S.k = kbase + col; S.i = G.i; S.sideR = G.sideR;
                     S.sigma = G.sigma; S.b = G.b;
-                    S.left = G.left; S.right = G.right; S.m = (G.left + G.right) / 2.0;
+                    S.left = __ldcg(&G.left); S.right = __ldcg(&G.right); S.m = (S.left + S.right) / 2.0;   // (a requeued bracket comes from another SM)
+                    S.steps = __ldcg(&G.steps);
                     S.nu1 = G.nu1; S.Kb = G.Kb; S.Kz = G.Kz;
-                    if (ROUND == 0) { S.steps = 0; S.wz2 = __dmul_rn(G.wz, G.wz); }
-                    else { S.steps = G.steps; S.wz2 = 1.0; S.knu0 = G.knu; S.krho = G.krho; S.sig2 = G.lambda; }
+                    if (ROUND == 0) S.wz2 = __dmul_rn(G.wz, G.wz);
+                    else { S.wz2 = 1.0; S.knu0 = G.knu; S.krho = G.krho; S.sig2 = G.lambda; }
+                    S.q = 0;
                     S.phase = PH_BISECT;
                 }
                 __syncwarp();
@@ -536,7 +609,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                 const bool act = S.phase == PH_BISECT;
                 sh.hot[warp] = act ? make_double2(S.sigma, S.m) : make_double2(0.0, 0.0);
                 sh.skip[warp] = (act && ROUND == 0) ? (long long)(S.i - 1) : -1;   // the re-shifted sigma_1 is not a pole
-                sh.act[warp] = act ? 1 : 0;
+                sh.act[warp] = act ? 1 : (S.phase == PH_PENDING ? 2 : 0);
             }
         }
         first = false;
@@ -544,19 +617,27 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
 
         // ================= per-thread copies of the sweep parameters =================
         unsigned actmask = 0;
+        bool waiting = false;
         unsigned fixmask = 0;
         int fmin = 0x7fffffff, fmax_ = -1;
 #pragma unroll
         for (int j = 0; j < NSLOT; ++j) {
             const long long sk = sh.skip[j];
-            if (sh.act[j] != 0) actmask |= 1u << j;
+            const int aj = sh.act[j];
+            if (aj == 1) actmask |= 1u << j;
+            if (aj == 2) waiting = true;
             if (sk >= 0) {
                 const int t_i = (int)(sk / BTL);
                 const int owner = (int)(((sk % BTL) % (2 * BT)) >> 1);
                 if (owner == tid) { fixmask |= 1u << j; fmin = min(fmin, t_i); fmax_ = max(fmax_, t_i); }
             }
         }
-        if (actmask == 0) break;
+        if (actmask == 0) {
+            if (!waiting) break;
+            __nanosleep(2000);     // only slots waiting for queued work: look again in a moment
+            __syncthreads();
+            continue;
+        }
         double acc[NSLOT];
 #pragma unroll
         for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
@@ -592,8 +673,8 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             // measured and costs the full-occupancy case more than the tail gains.)
 #pragma unroll
             for (int j = 0; j < NSLOT; ++j) {
-                // Round 1 has few eigenpairs (~1 %), spread thinly over the CTAs: skip idle slots there with a
-                // CTA-uniform branch.  (In round 0 the same test costs the full-occupancy loop 2-4 %: measured.)
+                // Few eigenpairs, spread thinly over the CTAs: skip idle slots with a CTA-uniform branch.
+                // (The same test costs the full-occupancy loop 2-4 %: measured.)
                 if (ROUND == 0 || ((actmask >> j) & 1u)) {
                     const double2 h = sh.hot[j];   // (sigma_j, m_j): broadcast LDS.128, reloaded per tile to save 32 registers
 #pragma unroll
@@ -707,7 +788,7 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
             }
         } else {
             BSlot S;                                   // identical copy in every thread
-            S.k = k; S.i = G.i; S.phase = PH_BISECT; S.sideR = sideR ? 1 : 0; S.steps = G.steps; S.pad_ = 0;
+            S.k = k; S.i = G.i; S.phase = PH_BISECT; S.sideR = sideR ? 1 : 0; S.steps = G.steps; S.q = 0;
             S.sigma = shift; S.wz2 = 1.0; S.b = R.rho; S.left = left; S.right = right; S.m = (left + right) / 2.0;
             S.nu1 = nu1new; S.Kb = G.Kb; S.Kz = G.Kz; S.knu0 = G.knu; S.krho = R.Krho; S.sig2 = sigma1;
             __syncthreads();                           // every thread has read G before thread 0 rewrites it in the finalize
@@ -903,20 +984,6 @@ k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_
 }
 
 // =====================================================================================================
-// Slots per CTA for round 0.  All NSLOT slots of a CTA are evaluated in every sweep, so a launch costs about
-// waves * NSLOT sweeps-worth of work with waves = ceil(cnt / (CTAs * NSLOT)): for small k-ranges (multi-GPU
-// shards, host-staged column blocks) 7 or 6 slots can pack the eigenpairs into fuller waves than 8.
-inline int pick_slots(int64_t cnt, int64_t ctas) {
-    int best = BJ;
-    int64_t best_cost = INT64_MAX;
-    for (int ns = BJ; ns >= BJ - 2; --ns) {
-        const int64_t waves = (cnt + ctas * ns - 1) / (ctas * ns);
-        const int64_t cost = waves * ns * 16 + (BJ - ns);          // tie -> more slots (less L2 traffic per term)
-        if (cost < best_cost) { best_cost = cost; best = ns; }
-    }
-    return best;
-}
-
 inline int configure_pipe_kernels() {
     const int smem = (int)sizeof(BisectShared);
     cudaError_t e;
@@ -940,27 +1007,41 @@ inline int launch_prep(int kind, const Problem &P, KState *ks, int64_t kbase, in
     return (int)cudaGetLastError();
 }
 // round 0: all READY eigenpairs of the block; round 1: the Remedy-3 list (its length is read on the device)
-template <int KIND>
-inline void launch_bisect_kind(int round, int nslot, int grid, int smem, cudaStream_t st, const Problem &P, const Outputs &O, KState *ks,
-                               int64_t kbase, int64_t cnt, int64_t *dlist, int64_t *rlist, unsigned long long *dcount) {
-    if (round == 1) k_bisect<KIND, 1, 8><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount);
-    else if (nslot == 8) k_bisect<KIND, 0, 8><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount);
-    else if (nslot == 7) k_bisect<KIND, 0, 7><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount);
-    else k_bisect<KIND, 0, 6><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount);
-}
+// requeue buffer entries k_bisect round 0 may need for a block of cnt eigenpairs (it stops time-slicing when the buffer is full)
+inline size_t bisect_queue_entries(int64_t cnt) { return (size_t)cnt * 24 + 8192; }
+
+// quantum: steps an eigenpair keeps its slot while others wait (0: no time slicing, < 0: chosen here);
+// window: time slicing starts when fewer than window x (all slots) eigenpairs are waiting; tag: unique per launch, != 0
 inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O, KState *ks, int64_t kbase, int64_t cnt,
-                         int64_t *dlist, int64_t *rlist, unsigned long long *dcount, int sm_count, cudaStream_t st) {
+                         int64_t *dlist, int64_t *rlist, unsigned long long *dcount, unsigned long long *queue, long long qcap,
+                         unsigned tag, int quantum, int window, int sm_count, cudaStream_t st) {
     const int smem = (int)sizeof(BisectShared);
     const int64_t cap = (int64_t)sm_count * BCTAS;
-    const int nslot = (round == 1) ? BJ : pick_slots(cnt, cap);
-    // one CTA per SM slot, but never more CTAs than there are groups of eigenpairs (round 1: one eigenpair per CTA where possible)
+    // Round 0: 8 slots per CTA unless the block has fewer than 8 (7) eigenpairs per CTA of a full grid -- then 7 (6)
+    // slots, and no more CTAs than groups of that size.  Round 1 (list length known to the device only): one
+    // eigenpair per CTA where possible.
+    const int nslot = (round == 1 || cnt > cap * (BJ - 1)) ? BJ : (cnt > cap * (BJ - 2) ? BJ - 1 : BJ - 2);
     const int64_t want = (round == 1) ? cnt : (cnt + nslot - 1) / nslot;
     const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-    switch (kind) {
-        case KIND_ARROW: launch_bisect_kind<KIND_ARROW>(round, nslot, grid, smem, st, P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
-        case KIND_DPR1: launch_bisect_kind<KIND_DPR1>(round, nslot, grid, smem, st, P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
-        default: launch_bisect_kind<KIND_HALF>(round, nslot, grid, smem, st, P, O, ks, kbase, cnt, dlist, rlist, dcount); break;
+    if (quantum < 0) {   // automatic time slice
+        const int64_t ntiles = P.Np / BTL;
+        // a switch costs a few microseconds of latency per slot: keep it small against quantum sweeps of ntiles tiles;
+        // and nothing ever waits when every eigenpair has a slot of its own from the start
+        quantum = (cnt <= (int64_t)grid * nslot) ? 0 : (int)std::min<int64_t>(32, std::max<int64_t>(8, 128 / std::max<int64_t>(1, ntiles)));
     }
+#define AH_LAUNCH_BISECT(KD, RD, NS) k_bisect<KD, RD, NS><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount, queue, qcap, tag, quantum, window)
+#define AH_LAUNCH_KIND(RD, NS)                                          \
+    switch (kind) {                                                     \
+        case KIND_ARROW: AH_LAUNCH_BISECT(KIND_ARROW, RD, NS); break;   \
+        case KIND_DPR1: AH_LAUNCH_BISECT(KIND_DPR1, RD, NS); break;     \
+        default: AH_LAUNCH_BISECT(KIND_HALF, RD, NS); break;            \
+    }
+    if (round == 1) { AH_LAUNCH_KIND(1, 8) }
+    else if (nslot == 8) { AH_LAUNCH_KIND(0, 8) }
+    else if (nslot == 7) { AH_LAUNCH_KIND(0, 7) }
+    else { AH_LAUNCH_KIND(0, 6) }
+#undef AH_LAUNCH_KIND
+#undef AH_LAUNCH_BISECT
     return (int)cudaGetLastError();
 }
 inline int launch_rem3_prep(int kind, const Problem &P, const Outputs &O, KState *ks, int64_t kbase, int64_t cnt, int64_t *rlist,
