@@ -37,7 +37,7 @@ class AhStats(C.Structure):
         ("launches", C.c_int64), ("n_fast", C.c_int64), ("n_full", C.c_int64), ("total_steps", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("prep_ms", C.c_double), ("bisect_ms", C.c_double), ("vec_ms", C.c_double), ("full_ms", C.c_double),
-        ("n_rem3", C.c_int64), ("rem3_ms", C.c_double),
+        ("n_rem3", C.c_int64), ("rem3_ms", C.c_double), ("host_pre_ms", C.c_double), ("host_post_ms", C.c_double),
     ]
 
     def asdict(self):

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -170,6 +171,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     using namespace ah;
     const int64_t N = L.N, cnt = k1 - k0 + 1;
     ctx->stats = ah_stats{};
+    const auto t_enter = std::chrono::steady_clock::now();
     AH_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if ((out->rowmap_u || out->rowmap_v) && ((out->U && out->U_mem != AH_MEM_DEVICE) || (out->V && out->V_mem != AH_MEM_DEVICE)))
@@ -298,6 +300,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         AH_CUDA(cudaEventCreate(&e));
         ctx->side_ev.push_back(e);
     }
+    ctx->stats.host_pre_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     for (int64_t c0 = 0, cc = 0; c0 < cnt; c0 += cc, ++nbuf) {
         cc = std::min(nbuf == 0 ? first : chunk, cnt - c0);
         const int slot = nbuf & 1;
@@ -429,6 +432,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     AH_CUDA(cudaEventRecord(ctx->ev[7], st));
     AH_CUDA(cudaStreamSynchronize(st));
     if (staged) AH_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    const auto t_synced = std::chrono::steady_clock::now();
     for (int c = 0; c < nchunks; ++c) {   // kernel times of every column block
         cudaEvent_t *E = &ctx->chunk_ev[5 * (size_t)c];
         float t = 0.f;
@@ -480,6 +484,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     for (int q = 0; q < n_count_reads; ++q) { n_full += (int64_t)ctx->hCounts[2 * q]; ctx->stats.n_rem3 += (int64_t)ctx->hCounts[2 * q + 1]; }
     ctx->stats.n_full = n_full;
     ctx->stats.n_fast = cnt - n_full;
+    ctx->stats.host_post_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_synced).count();
     return AH_OK;
 }
 

@@ -142,6 +142,19 @@ __device__ __forceinline__ double rcp_fast(double t) {
     return __fma_rn(r0, p, r0);
 }
 
+// w / d without nvcc's IEEE-division sequence (whose slow-path test is a branch per quotient and keeps the
+// compiler from interleaving independent quotients): q0 = w * (1/d to ~1 ulp), one residual correction
+// q = q0 + (w - d*q0)/d  (Markstein).  q is w/d to half an ulp + 2^-100: the correctly rounded quotient.
+// Valid while d, 1/d and q stay in the normal range; `ok` is cleared otherwise (the caller divides exactly then).
+__device__ __forceinline__ double div_fast(double w, double d, bool &ok) {
+    const double y = rcp_fast(d);
+    const double q0 = __dmul_rn(w, y);
+    const double r = __fma_rn(-d, q0, w);
+    const double ad = fabs(d), aq = fabs(q0);
+    ok = ok && (ad > 1.0e-290) && (ad < 1.0e290) && (aq > 1.0e-290) && (aq < 1.0e290);
+    return __fma_rn(r, y, q0);
+}
+
 // One term of the inverse-arrow / inverse-DPR1 secular sum, written on the ORIGINAL data:
 //   z'_l^2 / (D'_l - m)  with  D'_l = 1/d,  z'_l^2 = w2 * wz^2 / d^2
 //   = wz^2 * w2 / (d * (1 - m*d))

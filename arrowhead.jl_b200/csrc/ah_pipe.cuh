@@ -922,10 +922,25 @@ k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_
             const double2 d2 = d2n, w2 = w2n;
             if (l0 + 2 * VT < Npi) { d2n = ldg2(D + l0 + 2 * VT); w2n = ldg2(W + l0 + 2 * VT); }
             const bool pair = l0 + 1 < Ni;
+            // all 2 x VJ quotients branch-free and interleaved; the exact division only where one leaves the normal range
+            double q0[VJ], q1[VJ];
+            bool ok = true;
 #pragma unroll
             for (int j = 0; j < VJ; ++j) {
-                const double v0 = __dmul_rn(__ddiv_rn(w2.x, __dadd_rn(dshift<KIND>(d2.x, sigma[j]), -mu[j])), inrm[j]);
-                const double v1 = __dmul_rn(__ddiv_rn(w2.y, __dadd_rn(dshift<KIND>(d2.y, sigma[j]), -mu[j])), inrm[j]);
+                q0[j] = div_fast(w2.x, __dadd_rn(dshift<KIND>(d2.x, sigma[j]), -mu[j]), ok);
+                q1[j] = div_fast(w2.y, __dadd_rn(dshift<KIND>(d2.y, sigma[j]), -mu[j]), ok);
+            }
+            if (!ok) {
+#pragma unroll
+                for (int j = 0; j < VJ; ++j) {
+                    q0[j] = __ddiv_rn(w2.x, __dadd_rn(dshift<KIND>(d2.x, sigma[j]), -mu[j]));
+                    q1[j] = __ddiv_rn(w2.y, __dadd_rn(dshift<KIND>(d2.y, sigma[j]), -mu[j]));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VJ; ++j) {
+                const double v0 = __dmul_rn(q0[j], inrm[j]);
+                const double v1 = __dmul_rn(q1[j], inrm[j]);
                 if (mode[j] == 1 && pair) {
                     *reinterpret_cast<double2 *>(ucol[j] + l0) = make_double2(v0, v1);
                 } else if (mode[j] != 0) {
@@ -946,13 +961,25 @@ k_vec(Problem P, Outputs O, const KState *__restrict__ ks, int64_t kbase, int64_
             rs[0] = O.rowscale_v[l0];
             if (l0 + 1 < N) rs[1] = O.rowscale_v[l0 + 1];
         }
+        double q[VJ][2];
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < VJ; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) q[j][h] = div_fast(wv[h], __dadd_rn(dshift<KIND>(dv[h], sigma[j]), -mu[j]), ok);
+        if (!ok) {
+#pragma unroll
+            for (int j = 0; j < VJ; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) q[j][h] = __ddiv_rn(wv[h], __dadd_rn(dshift<KIND>(dv[h], sigma[j]), -mu[j]));
+        }
 #pragma unroll
         for (int j = 0; j < VJ; ++j) {
             double *const vec = (KIND == KIND_HALF) ? vcol[j] : ucol[j];
             double v[2], vo[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                v[h] = __dmul_rn(__ddiv_rn(wv[h], __dadd_rn(dshift<KIND>(dv[h], sigma[j]), -mu[j])), inrm[j]);
+                v[h] = __dmul_rn(q[j][h], inrm[j]);
                 vo[h] = (KIND == KIND_HALF && O.rowscale_v) ? __dmul_rn(v[h], rs[h]) : v[h];
             }
             if (vec) {

@@ -180,7 +180,7 @@ def run_ours(args):
     k0, k1 = ab.k_partition(n, world, rank)
     cnt = k1 - k0 + 1
     U = torch.empty((cnt, n), dtype=torch.float64, device=dev)          # this rank's columns of U (column-major block)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    flush = torch.empty(32 << 20, dtype=torch.float64, device=dev)      # 256 MB > 126 MB L2 (float64: torch's 1-byte fill kernel is 10x slower than the memory)
 
     def barrier():
         if dist is not None:

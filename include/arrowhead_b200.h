@@ -103,6 +103,8 @@ typedef struct ah_stats {
     double  prep_ms, bisect_ms, vec_ms, full_ms;   /* per-kernel device time: k_prep, k_bisect (+ Remedy-3 round), k_vec, k_full */
     int64_t n_rem3;           /* eigenpairs that took the Remedy-3 round of the fast path (counted in n_fast) */
     double  rem3_ms;          /* k_rem3_prep + k_bisect round 1 (device time on the side stream; overlaps k_vec) */
+    double  host_pre_ms;      /* host wall time from entry to the first kernel launch (padding, H2D enqueue, allocation) */
+    double  host_post_ms;     /* host wall time after the device finished (unpacking the per-k outputs) */
 } ah_stats;
 
 /* ---- context ---------------------------------------------------------------------------------- */
