@@ -55,7 +55,8 @@ struct ah_ctx {
     DevBuf dD, dW, dW2, dKs, dRList, dZ, dMap1, dMap2, dScale, dOut, dList, dCount, dQueue, dStage[2];
     void *hPinned = nullptr;  // pinned bounce buffer for the per-k outputs
     size_t hPinnedCap = 0;
-    std::vector<double> hPadD, hPadW, hPadW2;
+    double *hIn = nullptr;      // pinned staging of the padded inputs D | w | w^2
+    size_t hInCap = 0;
     cublasHandle_t blas = nullptr;       // created on first use (ah_dgemm_batched)
     DevBuf dPtrA, dPtrB, dPtrC, dIdx, dBatchA;
     std::vector<cudaEvent_t> chunk_ev;   // 5 timing events per column block of the current call
@@ -183,12 +184,18 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     // below every real pole (so no shift or bisection point can hit them) and carry weight 0.
     int rc;
     const int64_t Np = ((N + ah::TILE_POLES - 1) / ah::TILE_POLES) * ah::TILE_POLES;
-    ctx->hPadD.assign((size_t)Np, 0.0);
-    ctx->hPadW.assign((size_t)Np, 0.0);
-    ctx->hPadW2.assign((size_t)Np, 0.0);
-    std::memcpy(ctx->hPadD.data(), hD, N * 8);
-    std::memcpy(ctx->hPadW.data(), hW, N * 8);
-    for (int64_t l = 0; l < N; ++l) ctx->hPadW2[l] = hW[l] * hW[l];   // one rounding, as z[k]^2 in the reference
+    // D | w | w^2 go through one pinned staging block and one copy (pageable sources are staged by the driver in
+    // small pieces: 3 x 256 KB took 50 us + 100 us of host time at n = 32768)
+    if ((size_t)(3 * Np * 8) > ctx->hInCap) {
+        if (ctx->hIn) cudaFreeHost(ctx->hIn);
+        ctx->hIn = nullptr; ctx->hInCap = 0;
+        if (cudaMallocHost((void **)&ctx->hIn, (size_t)(3 * Np * 8)) != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_NOMEM, "cudaMallocHost failed"); }
+        ctx->hInCap = (size_t)(3 * Np * 8);
+    }
+    double *hPadD = ctx->hIn, *hPadW = ctx->hIn + Np, *hPadW2 = ctx->hIn + 2 * Np;
+    std::memcpy(hPadD, hD, N * 8);
+    std::memcpy(hPadW, hW, N * 8);
+    for (int64_t l = 0; l < N; ++l) hPadW2[l] = hW[l] * hW[l];   // one rounding, as z[k]^2 in the reference
     double pad;
     if (L.kind == KIND_HALF) {
         pad = hD[N - 1] / 2.0;
@@ -198,18 +205,14 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         pad = hD[N - 1] - span;
         if (!std::isfinite(pad)) pad = -1.7976931348623157e308;
     }
-    for (int64_t l = N; l < Np; ++l) ctx->hPadD[l] = pad;
-    if ((rc = ensure(ctx, ctx->dD, Np * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->dW, Np * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->dW2, Np * 8))) return rc;
+    for (int64_t l = N; l < Np; ++l) { hPadD[l] = pad; hPadW[l] = 0.0; hPadW2[l] = 0.0; }
+    if ((rc = ensure(ctx, ctx->dD, 3 * Np * 8))) return rc;
     AH_CUDA(cudaEventRecord(ctx->ev[0], st));
-    AH_CUDA(cudaMemcpyAsync(ctx->dD.p, ctx->hPadD.data(), Np * 8, cudaMemcpyHostToDevice, st));
-    AH_CUDA(cudaMemcpyAsync(ctx->dW.p, ctx->hPadW.data(), Np * 8, cudaMemcpyHostToDevice, st));
-    AH_CUDA(cudaMemcpyAsync(ctx->dW2.p, ctx->hPadW2.data(), Np * 8, cudaMemcpyHostToDevice, st));
+    AH_CUDA(cudaMemcpyAsync(ctx->dD.p, ctx->hIn, 3 * Np * 8, cudaMemcpyHostToDevice, st));
     ctx->stats.h2d_bytes += 3 * Np * 8;
     P.D = (const double *)ctx->dD.p;
-    P.w = (const double *)ctx->dW.p;
-    P.w2 = (const double *)ctx->dW2.p;
+    P.w = P.D + Np;
+    P.w2 = P.D + 2 * Np;
     P.Np = Np;
     P.pad = pad;
     P.z = nullptr;
@@ -338,11 +341,12 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             rc = ah::launch_bisect(L.kind, 0, P, Oc, ks, kb, cc, dlist, rlist, dcount, (unsigned long long *)ctx->dQueue.p,
                                    (long long)(ctx->dQueue.cap / 8), ctx->bisect_tag, ctx->quantum, ctx->window, ctx->sm_count, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect launch");
+            ctx->stats.launches += 2;   // k_prep, k_bisect round 0
             AH_CUDA(cudaEventRecord(E[2], st));
             // Remedy 3 on the fast path: re-shift (k_rem3_prep) and bisect again (round 1) for the ~1 % of eigenpairs
             // on the list (its length lives on the device).  The round is short and latency-bound, so it runs on a
             // high-priority side stream BESIDE the eigenvector kernel of everything round 0 finished; the listed
-            // eigenpairs get their vectors in a second, list-driven k_vec after the join.
+            // eigenpairs get their vectors from a second, list-driven k_vec on the side stream, too.
             {
                 const int64_t guess = std::max<int64_t>(1, std::min<int64_t>(cc, (int64_t)ctx->sm_count * 2 * ah::BJ));   // full grid; idle slots are skipped
                 const bool overlap = wantU || wantV;
@@ -360,12 +364,13 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                 AH_CUDA(cudaEventRecord(SE[1], rs));
                 ctx->stats.launches += 2;
                 if (overlap) {
+                    // the listed eigenpairs get their vectors on the side stream, too (other columns than the main k_vec's)
+                    rc = ah::launch_vec(L.kind, P, Oc, ks, kb, guess, rlist, dcount + 2, ctx->sm_count, rs);
+                    if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_vec (Remedy-3 list) launch");
                     AH_CUDA(cudaEventRecord(ctx->ev_join, rs));
                     rc = ah::launch_vec(L.kind, P, Oc, ks, kb, cc, nullptr, nullptr, ctx->sm_count, st);
                     if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_vec launch");
                     AH_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-                    rc = ah::launch_vec(L.kind, P, Oc, ks, kb, guess, rlist, dcount + 2, ctx->sm_count, st);
-                    if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_vec (Remedy-3 list) launch");
                     ctx->stats.launches += 2;
                 }
             }
@@ -647,6 +652,7 @@ void ah_destroy(ah_ctx *ctx) {
                       &ctx->dCount, &ctx->dQueue, &ctx->dStage[0], &ctx->dStage[1]})
         if (b->p) cudaFree(b->p);
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+    if (ctx->hIn) cudaFreeHost(ctx->hIn);
     if (ctx->hCounts) cudaFreeHost(ctx->hCounts);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);

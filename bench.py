@@ -254,7 +254,6 @@ def run_ours(args):
         "terms_per_launch": terms_fast, "kernel_ms": t_main * 1e3, "fast_eigenpairs": int(n_fast),
         "hbm_store": {"kernel": "k_vec", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                       "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-        "alt_frac_10_instr_per_term": 10.0 / FP64_INSTR_PER_TERM * achieved_tf / peak_tf,
     }
 
     # ---- end to end: host D,z in, eigenvalues + Info + this rank's eigenvectors out to pinned host memory
