@@ -388,7 +388,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=32768)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=32768,
+                    help="matrix order (under torchrun spell it --size: its own parser treats --n as an abbreviation)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="symarrow", choices=["symarrow", "tdc"])

@@ -517,6 +517,45 @@ def test_tdc_device_wilkinson_w21_and_duplicate_deflation(gpu_ctx, golden):
     assert np.max(np.abs(np.sort(Eref.values) - np.sort(Rref.values))) <= 50 * EPS
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("kind", ["symarrow", "symdpr1", "halfarrow"])
+def test_time_slicing_is_bitwise_schedule_independent(kind, monkeypatch):
+    """k_bisect hands eigenpairs back to a global FIFO after `quantum` steps when others wait.
+    Which slot advances an eigenpair, and when, must not change a single bit: no time slicing, the default, and a
+    pathological schedule (every eigenpair requeued after every step, from the first sweep on) give identical results."""
+    import torch
+    n = 7000                                  # ~3 eigenpairs per slot on a B200: there is always something waiting
+    outs = []
+    for quantum, window in (("0", "2"), (None, None), ("1", "100000"), ("5", "3")):
+        for name, val in (("ARROWHEAD_B200_QUANTUM", quantum), ("ARROWHEAD_B200_WINDOW", window)):
+            if val is None:
+                monkeypatch.delenv(name, raising=False)
+            else:
+                monkeypatch.setenv(name, val)
+        ctx = ab.Context(0)                   # the knobs are read when the context is created
+        try:
+            U = torch.empty((n, n), dtype=torch.float64, device="cuda")
+            if kind == "symarrow":
+                D, z, a = gen_symarrow(n, seed=11)
+                r = ctx.symarrow(D, z, a, vectors=False, U_dev=U.data_ptr(), ldu=n)
+            elif kind == "symdpr1":
+                D, u, rho = gen_symdpr1(n, seed=11)
+                r = ctx.symdpr1(D, u, rho, vectors=False, U_dev=U.data_ptr(), ldu=n)
+            else:
+                D, z = gen_halfarrow(n - 1, True, seed=11)
+                r = ctx.halfarrow(D, z, vectors=False, V_dev=U.data_ptr(), ldv=n)
+            torch.cuda.synchronize()
+            outs.append((r.lam.copy(), r.steps.copy(), r.knu.copy(), r.krho.copy(), r.status.copy(), U))
+        finally:
+            ctx.close()
+    ref = outs[0]
+    assert ref[1].sum() > 40 * n              # real bisections happened
+    for o in outs[1:]:
+        for a_, b_ in zip(ref[:5], o[:5]):
+            assert np.array_equal(a_, b_, equal_nan=True)
+        assert torch.equal(ref[5], o[5])
+
+
 def test_remedy3_direct_and_ring_paths_agree_bitwise(gpu_ctx):
     """Short Remedy-3 lists are bisected by k_rem3_prep itself, long ones by round 1 of the persistent kernel; both
     use the same summation order, so sharding a problem (short lists) must reproduce the unsharded run (long list)."""
