@@ -302,6 +302,9 @@ constexpr int BTL = BT * BE;     // poles per tile (2048)
 #define AH_BS 4
 #endif
 constexpr int BS = AH_BS;        // ring stages
+#ifndef AH_QSHIFT
+#define AH_QSHIFT 2
+#endif
 #ifndef AH_REM3_DIRECT_MAX
 #define AH_REM3_DIRECT_MAX 128
 #endif
@@ -468,6 +471,9 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
     const unsigned long long ucnt = (unsigned long long)cnt;
     const unsigned long long slots_total = (unsigned long long)gridDim.x * NSLOT;
     unsigned long long *const tickets = dcount + (ROUND == 0 ? 1 : 3);
+    // shortest slice near convergence: a switch costs ~2.5 us of latency, so not more often than every ~32 tiles, and
+    // not shortened at all when the sweeps are short (measured: n = 8192 loses 3 %, n >= 16384 gains 1-3 %)
+    const int qmin = ntiles >= 16 ? max(1, 32 / ntiles) : quantum;
 
     bool wrapped = false;    // g_issue has wrapped around 2^32 at least once
     uint32_t g_issue = 0;    // tiles issued (thread 0 only); wraps mod 2^32, a multiple of 2*BS -> parities stay consistent
@@ -529,8 +535,14 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                         // time slice used up and others are waiting -> back of the queue
                         int swap = 0;
                         const int qv = S.q;
+                        // The slice shrinks as the eigenpair nears convergence (steps left ~ exponent of the bracket width
+                        // over 2 eps max|bracket|): time-sliced eigenpairs then finish within a step or two of each other
+                        // instead of a quantum or two, which is what the launch waits for at its end.
+                        const double wdt = S.right - S.left, mxb = fmax(fabs(S.left), fabs(S.right));
+                        const int left_est = ((__double2hiint(wdt) >> 20) & 0x7ff) - ((__double2hiint(mxb) >> 20) & 0x7ff) + 51;
+                        const int qeff = min(quantum, max(qmin, left_est >> AH_QSHIFT));
                         __syncwarp();
-                        if (ROUND == 0 && quantum > 0 && qv >= quantum) {
+                        if (ROUND == 0 && quantum > 0 && qv >= qeff) {
                             if (lane == 0) {
                                 const unsigned long long head = ld_volatile(tickets), nreq = ld_volatile(dcount + 4);
                                 const unsigned long long tail = ucnt + nreq;
