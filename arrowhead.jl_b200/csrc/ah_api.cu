@@ -260,7 +260,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     if ((rc = ensure(ctx, ctx->dList, cnt * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dKs, (size_t)cnt * sizeof(ah::KState)))) return rc;
     if ((rc = ensure(ctx, ctx->dRList, cnt * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->dCount, 256))) return rc;
+    if ((rc = ensure(ctx, ctx->dCount, 2048))) return rc;
     {   // requeue FIFO of k_bisect's time slicing; entries carry a per-launch tag, so it is cleared only when (re)allocated
         const size_t qbytes = ah::bisect_queue_entries(cnt) * 8;
         if (qbytes > ctx->dQueue.cap) {
@@ -330,7 +330,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         if (ctx->mode == 0) {
             KState *ks = (KState *)ctx->dKs.p;
             int64_t *rlist = (int64_t *)ctx->dRList.p;
-            AH_CUDA(cudaMemsetAsync(dcount, 0, 64, st));
+            AH_CUDA(cudaMemsetAsync(dcount, 0, 128 + 256 * 4, st));
             rc = ah::launch_prep(L.kind, P, ks, kb, cc, dlist, dcount, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_prep launch");
             AH_CUDA(cudaEventRecord(E[1], st));

@@ -37,7 +37,7 @@
 namespace ah {
 
 enum : int { KS_READY = 0, KS_HANDOFF = 1, KS_DONE = 2, KS_REM3 = 3, KS_REM3_READY = 4, KS_DONE1 = 5 };   // DONE1: finished in round 1
-// counters (unsigned long long[8]): [0] hand-over list length, [1] k_bisect round-0 ticket counter,
+// counters (unsigned long long[16] + unsigned[256] per-SM arrival counts of k_bisect round 0): [0] hand-over list length, [1] k_bisect round-0 ticket counter,
 //                                   [2] Remedy-3 list length,   [3] k_bisect round-1 ticket counter,
 //                                   [4] round-0 requeue count,  [5] round-0 eigenpairs finished
 
@@ -302,6 +302,12 @@ constexpr int BTL = BT * BE;     // poles per tile (2048)
 #define AH_BS 4
 #endif
 constexpr int BS = AH_BS;        // ring stages
+#ifndef AH_STAGGER
+#define AH_STAGGER 1
+#endif
+#ifndef AH_STAGGER_NS_PER_TILE
+#define AH_STAGGER_NS_PER_TILE 600   // half of the ~1.2 us a tile takes with 8 slots
+#endif
 #ifndef AH_QSHIFT
 #define AH_QSHIFT 2
 #endif
@@ -466,6 +472,25 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
     }
     if (tid < NSLOT) { sh.slot[tid].phase = PH_FREE; sh.skip[tid] = -1; sh.act[tid] = 0; sh.hot[tid] = make_double2(0.0, 0.0); }
     if (ROUND == 1) { cnt = (int64_t)dcount[2]; quantum = 0; }   // round 1 works through the (short) Remedy-3 list
+#if AH_STAGGER
+    // Every sweep is ntiles tiles for every CTA, so the two CTAs of an SM would reach their sweep boundaries (reduce,
+    // decide, refill: ~2 us without FP64 work) together for the whole launch.  The second CTA to arrive on an SM starts
+    // half a sweep late instead, and each then computes through the other's boundary.
+    if (ROUND == 0 && tid == 0 && ntiles >= 4) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned *const arrivals = reinterpret_cast<unsigned *>(dcount + 16);
+        if (atomicAdd(&arrivals[smid & 255u], 1u) & 1u) {
+            const unsigned long long wait_ns = (unsigned long long)ntiles * AH_STAGGER_NS_PER_TILE;
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                __nanosleep(500);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            } while (t1 - t0 < wait_ns);
+        }
+    }
+#endif
     __syncthreads();
     if (ROUND == 1 && cnt <= REM3_DIRECT_MAX) return;   // short list: k_rem3_prep has bisected it directly
     const unsigned long long ucnt = (unsigned long long)cnt;
