@@ -51,7 +51,7 @@ EXPORTS = [
     "ah_memcpy_d2h", "ah_memcpy_h2d", "ah_set_identity", "ah_apply_givens_rows", "ah_gather_permuted",
     "ah_scale_rows_phase", "ah_symarrow_eigvals_dd", "ah_symarrow_eigen_batched", "ah_gather_elements", "ah_gather_permuted_batched",
     "ah_copy2d_batched", "ah_dgemm_batched",
-    "ah_measure_fp64_peak", "ah_measure_store_bw",
+    "ah_measure_fp64_peak", "ah_measure_term_peak", "ah_measure_store_bw",
 ]
 
 
@@ -101,6 +101,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ah_dgemm_batched.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, u64p, C.c_int64, u64p, C.c_int64, u64p, C.c_int64]
     lib.ah_scale_rows_phase.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, _dp, C.c_int, C.c_int64, C.c_int64]
     lib.ah_measure_fp64_peak.argtypes = [vp, _dp, _dp]
+    lib.ah_measure_term_peak.argtypes = [vp, _dp, _dp]
     lib.ah_measure_store_bw.argtypes = [vp, C.c_int64, _dp]
     for name in EXPORTS:
         fn = getattr(lib, name)
@@ -323,6 +324,11 @@ class Context:
     def measure_fp64_peak(self):
         g, ms = C.c_double(), C.c_double()
         self._check(self.lib.ah_measure_fp64_peak(self.handle, C.byref(g), C.byref(ms)))
+        return g.value, ms.value
+
+    def measure_term_peak(self):
+        g, ms = C.c_double(), C.c_double()
+        self._check(self.lib.ah_measure_term_peak(self.handle, C.byref(g), C.byref(ms)))
         return g.value, ms.value
 
     def measure_store_bw(self, nbytes):

@@ -588,6 +588,27 @@ __global__ void k_dfma_burst(double *out, int iters, double a, double b) {
     }
     out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
+// The instruction mix of k_bisect's inner block from registers only: 4 poles x 8 (sigma, m) pairs = 32 independent
+// secular terms per iteration (7 FP64-pipe instructions + 1 MUFU.RCP64H each), no memory traffic, no barriers.
+__global__ void __launch_bounds__(256, 2) k_term_burst(double *out, int iters, double d0, double s0, double m0) {
+    double Dv[4], sg[8], mm[8], acc[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) Dv[e] = d0 + 1e-3 * e + 1e-9 * threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sg[j] = s0 + 1e-2 * j; mm[j] = m0 * (1.0 + 1e-2 * j); acc[j] = 0.0; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Dv[e] = __dadd_rn(Dv[e], 1e-9);    // new "tile" (4 extra DADD per 224 instructions)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j] = ah::secular_term_acc(acc[j], __dadd_rn(Dv[e], -sg[j]), mm[j], 1.0 + 1e-3 * e);
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += acc[j];
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
 __global__ void k_store_stream(double2 *dst, int64_t n2, double v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
         dst[i] = make_double2(v, v);
@@ -1078,6 +1099,29 @@ int ah_measure_fp64_peak(ah_ctx *ctx, double *ginstr_per_s, double *elapsed_ms) 
     AH_CUDA(cudaGetLastError());
     const double instr = (double)threads * blocks * (double)iters * 8.0;
     *ginstr_per_s = instr / (best * 1e-3) / 1e9;
+    if (elapsed_ms) *elapsed_ms = best;
+    return AH_OK;
+}
+int ah_measure_term_peak(ah_ctx *ctx, double *gterms_per_s, double *elapsed_ms) {
+    if (!ctx || !gterms_per_s) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    const int threads = 256, blocks = ctx->sm_count * 2, iters = 1 << 13;
+    int rc;
+    if ((rc = ensure(ctx, ctx->dStage[0], (size_t)threads * blocks * 8))) return rc;
+    double *o = (double *)ctx->dStage[0].p;
+    k_term_burst<<<blocks, threads, 0, ctx->stream>>>(o, 64, 0.5, 0.25, 0.125);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        AH_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+        k_term_burst<<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.5, 0.25, 0.125);
+        AH_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        AH_CUDA(cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0.f;
+        AH_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        best = std::min(best, ms);
+    }
+    AH_CUDA(cudaGetLastError());
+    *gterms_per_s = (double)threads * blocks * (double)iters * 32.0 / (best * 1e-3) / 1e9;
     if (elapsed_ms) *elapsed_ms = best;
     return AH_OK;
 }

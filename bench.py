@@ -192,6 +192,7 @@ def run_ours(args):
         return ctx.symarrow(D, z, a, k0=k0, k1=k1, vectors=False, U_dev=U.data_ptr(), ldu=n)
 
     fp64_ginstr, _ = ctx.measure_fp64_peak()
+    term_gps, _ = ctx.measure_term_peak()      # the inner block's instruction mix from registers only
     for _ in range(max(args.warmup, 3)):
         res = step()
     sampler = ClockSampler(physical_gpu_index(local_rank))
@@ -252,6 +253,10 @@ def run_ours(args):
                "eigenpair / device time of k_bisect (round 0 + the Remedy-3 round, CUDA events on their streams inside "
                "the timed region); peak = dependent-free DFMA burst measured live (MEASURED_PEAKS.json has no FP64 entry)",
         "terms_per_launch": terms_fast, "kernel_ms": t_main * 1e3, "fast_eigenpairs": int(n_fast),
+        "term_burst": {"gterms_per_s": term_gps, "achieved_gterms_per_s": terms_fast / t_main / 1e9,
+                       "frac": terms_fast / t_main / 1e9 / term_gps,
+                       "what": "secular terms/s of the same 7 FP64 + 1 MUFU.RCP64H mix from registers only (no tiles, no sweep "
+                               "boundaries): what the ring, the barriers and the work distribution cost"},
         "hbm_store": {"kernel": "k_vec", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                       "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
     }

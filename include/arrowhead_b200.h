@@ -195,6 +195,9 @@ int ah_scale_rows_phase(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const doub
 /* Dependent-free DFMA burst on every SM: returns FP64-pipe instruction issue rate in
  * 1e9 warp-lane-instructions/s (x2 = GFLOP/s) and the elapsed ms. */
 int ah_measure_fp64_peak(ah_ctx *ctx, double *ginstr_per_s, double *elapsed_ms);
+/* The same for the instruction mix of the bisection term (7 FP64-pipe instructions + 1 MUFU.RCP64H per secular term,
+ * 32 independent terms per thread and iteration, registers only): 1e9 terms/s.  The ceiling of k_bisect's inner block. */
+int ah_measure_term_peak(ah_ctx *ctx, double *gterms_per_s, double *elapsed_ms);
 /* streaming store of `bytes` to device memory: GB/s */
 int ah_measure_store_bw(ah_ctx *ctx, int64_t bytes, double *gb_per_s);
 
