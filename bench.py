@@ -54,6 +54,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.mask, self.stop_flag, self.max_mhz, self.ok = index, [], 0, False, None, False
+        self.interval = 0.01
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -76,7 +77,7 @@ class ClockSampler(threading.Thread):
                     self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(self.interval)
 
     def summary(self):
         if not self.ok or not self.samples:

@@ -38,3 +38,21 @@ for with_flush in (True, False):
     t1 = time.perf_counter()
     print(f"n={n}/{world} flush={with_flush}: events {e0.elapsed_time(e1)/K:.3f} ms/step, wall {(t1-t0)/K*1e3:.3f}, "
           f"symarrow() wall {wall_call/K*1e3:.3f}, kernels {kern/K:.3f}, stats={ {k: round(v,3) for k,v in r.stats.items() if k.endswith('_ms')} }")
+
+# ---- the same steps while NVML is polled from a second thread (bench.py's clock sampler)
+if len(sys.argv) > 3:
+    import threading
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    for interval in (0.01, 0.05):
+        smp = bench.ClockSampler(0)
+        smp.interval = interval
+        smp.start()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(K * 4):
+            flush.zero_()
+            r = ctx.symarrow(D, z, a, k0=k0, k1=k1, vectors=False, U_dev=U.data_ptr(), ldu=n)
+        e1.record(); torch.cuda.synchronize()
+        smp.stop_flag = True; smp.join()
+        print(f"with NVML sampler every {interval * 1e3:.0f} ms: events {e0.elapsed_time(e1) / (K * 4):.3f} ms/step ({len(smp.samples)} samples)")
