@@ -1,4 +1,4 @@
-// ah_pipe.cuh -- the fast path: standard (no-remedy, binary64) eigenpairs as a three-kernel pipeline.
+// ah_pipe.cuh -- the fast path: binary64 eigenpairs (standard ones and Remedy 3) as a pipeline of kernels.
 //
 // Every O(N) loop of the reference's per-k solver is a "sweep" over the poles l = 0..N-1:
 //
@@ -24,9 +24,12 @@
 // and redoes its four terms without the pole afterwards (a rare, warp-divergent side path).
 // A sweep ends with a fixed-order reduction (thread-sequential, xor-shuffle tree, warps 0..7); warp j
 // then advances slot j's bisection state, finalises a converged eigenpair (Knu test, Remedy-1 test) and
-// pulls the next k from a global counter, so all 8 slots stay busy until the work runs out.
-// Anything non-standard (double-double needed, Knu > tolnu -> Remedy 3, Remedy 1, |nu| = Inf) is
-// appended to a hand-over list and solved by k_full (ah_full.cuh).
+// takes the next work ticket; towards the end of a launch eigenpairs are time-sliced through a global
+// FIFO so that all slots stay busy until (almost) the last sweep (see the comment above k_bisect).
+// Knu > tolnu (Remedy 3, ~1 % of the eigenpairs) goes through k_rem3_prep and a second round of k_bisect
+// on the re-shifted inverse; anything else that is non-standard (double-double needed, Remedy 1,
+// |nu| = Inf, a Remedy 3 beyond its plain branch) is appended to a hand-over list and solved by k_full
+// (ah_full.cuh).
 #pragma once
 #include "ah_device.cuh"
 #include "ah_full.cuh"
