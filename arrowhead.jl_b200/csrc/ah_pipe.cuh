@@ -305,6 +305,9 @@ constexpr int BTL = BT * BE;     // poles per tile (2048)
 #define AH_BS 4
 #endif
 constexpr int BS = AH_BS;        // ring stages
+#ifndef AH_R1_CTAS_PER_SM
+#define AH_R1_CTAS_PER_SM 1
+#endif
 #ifndef AH_STAGGER
 #define AH_STAGGER 1
 #endif
@@ -1089,7 +1092,10 @@ inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O
     // eigenpair per CTA where possible.
     const int nslot = (round == 1 || cnt > cap * (BJ - 1)) ? BJ : (cnt > cap * (BJ - 2) ? BJ - 1 : BJ - 2);
     const int64_t want = (round == 1) ? cnt : (cnt + nslot - 1) / nslot;
-    const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    // Round 1 runs beside k_vec (two CTAs of 30 K registers per SM): one CTA per SM leaves room for one of them
+    // (measured: the k_vec span shrinks from 2.54 to 2.40 ms at n = 32768; half a CTA per SM makes the round itself too long)
+    const int64_t gcap = (round == 1) ? (int64_t)sm_count * AH_R1_CTAS_PER_SM : cap;
+    const int grid = (int)(want < gcap ? (want < 1 ? 1 : want) : gcap);
     if (quantum < 0) {   // automatic time slice
         const int64_t ntiles = P.Np / BTL;
         // a switch costs a few microseconds of latency per slot: keep it small against quantum sweeps of ntiles tiles;

@@ -18,7 +18,7 @@ best = None
 for rep in range(6):
     s = ctx.symarrow(D, z, a, k0=k0, k1=k1, vectors=False, U_dev=U.data_ptr(), ldu=n).stats
     if rep >= 2 and (best is None or s["kernel_ms"] < best["kernel_ms"]): best = s
-print("kernel=%%.3f bisect=%%.3f prep=%%.3f vec=%%.3f" %% (best["kernel_ms"], best["bisect_ms"], best["prep_ms"], best["vec_ms"]))
+print("kernel=%%.3f bisect=%%.3f prep=%%.3f vec=%%.3f rem3=%%.3f" %% (best["kernel_ms"], best["bisect_ms"], best["prep_ms"], best["vec_ms"], best["rem3_ms"]))
 ''' % (ROOT, ROOT)
 libs = sys.argv[1:3]
 n = sys.argv[3] if len(sys.argv) > 3 else "32768"
