@@ -46,7 +46,7 @@ class AhStats(C.Structure):
 
 EXPORTS = [
     "ah_version", "ah_create", "ah_destroy", "ah_last_error", "ah_set_stream", "ah_get_stats", "ah_set_mode",
-    "ah_symarrow_eigen", "ah_symdpr1_eigen", "ah_halfarrow_svd",
+    "ah_symarrow_eigen", "ah_symdpr1_eigen", "ah_halfarrow_svd", "ah_resolve",
     "ah_device_malloc", "ah_device_free", "ah_host_alloc_pinned", "ah_host_free_pinned",
     "ah_memcpy_d2h", "ah_memcpy_h2d", "ah_set_identity", "ah_apply_givens_rows", "ah_gather_permuted",
     "ah_scale_rows_phase", "ah_symarrow_eigvals_dd", "ah_symarrow_eigen_batched", "ah_gather_elements", "ah_gather_permuted_batched",
@@ -81,6 +81,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ah_symarrow_eigen.argtypes = [vp, C.c_int64, _dp, _dp, C.c_double, _dp, C.c_int64, C.c_int64, C.POINTER(AhResult)]
     lib.ah_symdpr1_eigen.argtypes = [vp, C.c_int64, _dp, _dp, C.c_double, _dp, C.c_int64, C.c_int64, C.POINTER(AhResult)]
     lib.ah_halfarrow_svd.argtypes = [vp, C.c_int64, C.c_int64, _dp, _dp, _dp, C.c_int64, C.c_int64, C.POINTER(AhResult)]
+    lib.ah_resolve.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(AhResult)]
     lib.ah_device_malloc.argtypes = [vp, C.POINTER(vp), C.c_int64]
     lib.ah_device_free.argtypes = [vp, vp]
     lib.ah_host_alloc_pinned.argtypes = [vp, C.POINTER(vp), C.c_int64]
@@ -208,6 +209,8 @@ class Context:
                 keep.append(a)
                 setattr(r, name, _ptr(a, _i64p if t is np.int64 else _dp))
         self._check(fn(self.handle, *args, int(k0), int(k1), C.byref(r)))
+        if fn is not self.lib.ah_resolve:
+            self._resident = (nrows_u, nrows_v)      # ah_resolve solves this problem again from the device-resident inputs
         res.stats = self.stats()
         return res
 
@@ -219,6 +222,16 @@ class Context:
         args = (C.c_int64(N), _ptr(D, _dp), _ptr(z, _dp), C.c_double(float(a)), _ptr(tau_a, _dp))
         return self._run(self.lib.ah_symarrow_eigen, args, k0, k1, N + 1, 0, vectors, U_dev, ldu, None, 0, rowmap, None,
                          None, U_host=U_host)
+
+    def resolve(self, k0, k1, vectors=True, U_dev=None, ldu=0, V_dev=None, ldv=0, rowmap_u=None, rowmap_v=None,
+                rowscale_v=None, U_host=None):
+        """ah_resolve: another k-range of the problem of the last symarrow / symdpr1 / halfarrow call on this context
+        (inputs still resident on the device: no validation, padding or host->device copy)."""
+        if getattr(self, "_resident", None) is None:
+            raise ArrowheadError(-1, "resolve(): no solve on this context yet")
+        nrows_u, nrows_v = self._resident
+        return self._run(self.lib.ah_resolve, (), k0, k1, nrows_u, nrows_v, vectors, U_dev, ldu, V_dev, ldv, rowmap_u,
+                         rowmap_v, rowscale_v, U_host=U_host)
 
     def symdpr1(self, D, u, rho, tau=None, k0=1, k1=None, vectors=True, U_dev=None, ldu=0, rowmap=None, U_host=None):
         D = np.ascontiguousarray(D, np.float64); u = np.ascontiguousarray(u, np.float64)

@@ -41,6 +41,10 @@ struct ah_ctx {
     int quantum = -1;           // k_bisect time slice (steps): < 0 automatic, 0 off (tuning knob ARROWHEAD_B200_QUANTUM)
     int window = 2;             // time slicing starts when fewer than window x slots eigenpairs wait (ARROWHEAD_B200_WINDOW)
     unsigned bisect_tag = 0;    // per-launch tag of the requeue FIFO entries
+    bool res_valid = false;     // dD / dZ still hold the inputs of the last solve (ah_resolve)
+    int res_kind = 0;
+    int64_t res_N = 0, res_nvec_u = 0, res_nvec_v = 0, res_kmax = 0;
+    ah::Problem res_P{};
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;   // high priority: the short Remedy-3 round runs beside k_vec
@@ -180,9 +184,10 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     if (out->U && out->ldu < (out->rowmap_u ? 1 : L.nvec_u)) return fail(ctx, AH_ERR_INVALID_ARG, "ldu too small");
     if (L.kind == KIND_HALF && out->V && out->ldv < (out->rowmap_v ? 1 : L.nvec_v)) return fail(ctx, AH_ERR_INVALID_ARG, "ldv too small");
 
+    int rc;
+    if (hD) {
     // ---- inputs -> device, padded to whole tiles of the fast kernel's ring.  Pad poles lie strictly
     // below every real pole (so no shift or bisection point can hit them) and carry weight 0.
-    int rc;
     const int64_t Np = ((N + ah::TILE_POLES - 1) / ah::TILE_POLES) * ah::TILE_POLES;
     // D | w | w^2 go through one pinned staging block and one copy (pageable sources are staged by the driver in
     // small pieces: 3 x 256 KB took 50 us + 100 us of host time at n = 32768)
@@ -221,6 +226,12 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         AH_CUDA(cudaMemcpyAsync(ctx->dZ.p, hZ, N * 8, cudaMemcpyHostToDevice, st));
         ctx->stats.h2d_bytes += N * 8;
         P.z = (const double *)ctx->dZ.p;
+    }
+        ctx->res_valid = true; ctx->res_kind = L.kind; ctx->res_N = L.N; ctx->res_nvec_u = L.nvec_u; ctx->res_nvec_v = L.nvec_v;
+        ctx->res_kmax = L.kmax; ctx->res_P = P;
+    } else {
+        // ah_resolve: the padded inputs of the previous solve are still on the device
+        AH_CUDA(cudaEventRecord(ctx->ev[0], st));
     }
     Outputs O{};
     if (out->rowmap_u) {
@@ -771,6 +782,15 @@ int ah_halfarrow_svd(ah_ctx *ctx, int64_t nd, int64_t nz, const double *D, const
     return run_solver(ctx, L, P, D, z1.data(), z, k0, k1, out);
 }
 
+int ah_resolve(ah_ctx *ctx, int64_t k0, int64_t k1, ah_result *out) {
+    if (!ctx) return AH_ERR_INVALID_ARG;
+    if (!out || !out->lambda) return fail(ctx, AH_ERR_INVALID_ARG, "null argument");
+    if (!ctx->res_valid) return fail(ctx, AH_ERR_INVALID_ARG, "ah_resolve: no inputs resident (call ah_symarrow_eigen / ah_symdpr1_eigen / ah_halfarrow_svd on this context first)");
+    if (k0 < 1 || k1 < k0 || k1 > ctx->res_kmax) return fail(ctx, AH_ERR_INVALID_ARG, "k-range outside 1.." + std::to_string(ctx->res_kmax));
+    Launch L{ctx->res_kind, ctx->res_N, ctx->res_nvec_u, ctx->res_nvec_v, ctx->res_kmax};
+    return run_solver(ctx, L, ctx->res_P, nullptr, nullptr, nullptr, k0, k1, out);
+}
+
 int ah_device_malloc(ah_ctx *ctx, void **dptr, int64_t bytes) {
     if (!ctx || !dptr || bytes < 0) return AH_ERR_INVALID_ARG;
     AH_CUDA(cudaSetDevice(ctx->device));
@@ -867,6 +887,7 @@ int ah_symarrow_eigen_batched(ah_ctx *ctx, int64_t nb, int64_t N, const double *
     cudaStream_t st = ctx->stream;
     const int64_t cnt = nb * (N + 1);
     int rc;
+    ctx->res_valid = false;
     if ((rc = ensure(ctx, ctx->dD, nb * N * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dW, nb * N * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dBatchA, 2 * nb * 8))) return rc;
@@ -934,6 +955,7 @@ int ah_symarrow_eigvals_dd(ah_ctx *ctx, int64_t N, const double *D, const double
     AH_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int64_t cnt = k1 - k0 + 1;
+    ctx->res_valid = false;
     if ((rc = ensure(ctx, ctx->dD, N * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dW, N * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dW2, N * 8))) return rc;

@@ -188,12 +188,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
+    def upload_and_step():       # the drop-in call: validates, pads and uploads D, z, then solves
         flush.zero_()
         return ctx.symarrow(D, z, a, k0=k0, k1=k1, vectors=False, U_dev=U.data_ptr(), ldu=n)
 
+    def step():                  # `value`: inputs already resident in HBM (ah_resolve); `e2e` below uploads them every step
+        flush.zero_()
+        return ctx.resolve(k0, k1, vectors=False, U_dev=U.data_ptr(), ldu=n)
+
     fp64_ginstr, _ = ctx.measure_fp64_peak()
     term_gps, _ = ctx.measure_term_peak()      # the inner block's instruction mix from registers only
+    res = upload_and_step()
     for _ in range(max(args.warmup, 3)):
         res = step()
     sampler = ClockSampler(physical_gpu_index(local_rank))
@@ -342,6 +347,7 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"SymArrow n={n} full eigen(), GenSymArrow-like rng(421), ordered, arrow top last",
                        "parallelism": f"k-range x{world}", "U": "device-resident, column blocks per rank",
+                       "inputs": "D, z (0.5 MB) resident in HBM, uploaded once before the timed region (ah_resolve); e2e uploads them every step",
                        "l2": "256 MB flush write before every step; the step itself streams out n^2*8 bytes >> L2",
                        "allgather_U_ms": allgather_ms,
                        "kernel_ms_per_step_rank0": kern_ms / args.steps,

@@ -134,6 +134,13 @@ int ah_symdpr1_eigen(ah_ctx *ctx, int64_t n, const double *D, const double *u, d
 int ah_halfarrow_svd(ah_ctx *ctx, int64_t nd, int64_t nz, const double *D, const double *z,
                      const double *tau, int64_t k0, int64_t k1, ah_result *out);
 
+/* Solve again, for another k-range (or into another U), the problem of the last ah_symarrow_eigen /
+ * ah_symdpr1_eigen / ah_halfarrow_svd call on this context: its padded inputs are still resident on the device, so
+ * validation, padding and the host->device copy are skipped.  Used by callers that sweep k-ranges over one matrix
+ * (host-staged blocks, repeated partial solves) and by bench.py's device-resident `value`.  Any other compute call on
+ * the context (batched solves, ah_symarrow_eigvals_dd) invalidates the resident inputs. */
+int ah_resolve(ah_ctx *ctx, int64_t k0, int64_t k1, ah_result *out);
+
 /* ---- device utilities for a resident U -------------------------------------------------------- */
 int ah_device_malloc(ah_ctx *ctx, void **dptr, int64_t bytes);
 int ah_device_free(ah_ctx *ctx, void *dptr);

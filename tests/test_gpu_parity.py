@@ -556,6 +556,53 @@ def test_time_slicing_is_bitwise_schedule_independent(kind, monkeypatch):
         assert torch.equal(ref[5], o[5])
 
 
+@pytest.mark.parametrize("kind", ["symarrow", "symdpr1", "halfarrow"])
+def test_resolve_reuses_the_resident_inputs_bitwise(kind):
+    """ah_resolve solves another k-range of the last problem without validation / padding / upload: identical to
+    the drop-in call with the same k-range; refused when nothing is resident or another call has overwritten it."""
+    import torch
+    ctx = ab.Context(0)
+    try:
+        with pytest.raises(ab.ArrowheadError):
+            ctx.resolve(1, 2, vectors=False)
+        n = 3000
+        if kind == "symarrow":
+            D, z, a = gen_symarrow(n, seed=3)
+            call = lambda k0, k1, U: ctx.symarrow(D, z, a, k0=k0, k1=k1, vectors=False, U_dev=U.data_ptr(), ldu=n)
+            again = lambda k0, k1, U: ctx.resolve(k0, k1, vectors=False, U_dev=U.data_ptr(), ldu=n)
+            kmax = n
+        elif kind == "symdpr1":
+            D, u, rho = gen_symdpr1(n, seed=3)
+            call = lambda k0, k1, U: ctx.symdpr1(D, u, rho, k0=k0, k1=k1, vectors=False, U_dev=U.data_ptr(), ldu=n)
+            again = lambda k0, k1, U: ctx.resolve(k0, k1, vectors=False, U_dev=U.data_ptr(), ldu=n)
+            kmax = n
+        else:
+            D, z = gen_halfarrow(n - 1, True, seed=3)
+            call = lambda k0, k1, U: ctx.halfarrow(D, z, k0=k0, k1=k1, vectors=False, V_dev=U.data_ptr(), ldv=n)
+            again = lambda k0, k1, U: ctx.resolve(k0, k1, vectors=False, V_dev=U.data_ptr(), ldv=n)
+            kmax = n
+        k0, k1 = 700, 2100
+        cnt = k1 - k0 + 1
+        U1 = torch.zeros((cnt, n), dtype=torch.float64, device="cuda")
+        U2 = torch.zeros((cnt, n), dtype=torch.float64, device="cuda")
+        call(1, 10, U1)                       # uploads the problem (another k-range)
+        r2 = again(k0, k1, U2)
+        r1 = call(k0, k1, U1)
+        torch.cuda.synchronize()
+        for name in ("lam", "sind", "kb", "kz", "knu", "krho", "qout", "steps", "status"):
+            assert np.array_equal(getattr(r1, name), getattr(r2, name), equal_nan=True), name
+        assert torch.equal(U1, U2)
+        assert r2.stats["h2d_bytes"] == 0
+        with pytest.raises(ab.ArrowheadError):
+            ctx.resolve(1, kmax + 1, vectors=False)
+        Db = np.sort(np.random.default_rng(1).random((2, 5)), axis=1)[:, ::-1].copy()
+        ctx.symarrow_batched(Db, np.ones((2, 5)), np.zeros(2))    # overwrites the resident inputs
+        with pytest.raises(ab.ArrowheadError):
+            ctx.resolve(1, 2, vectors=False)
+    finally:
+        ctx.close()
+
+
 def test_remedy3_direct_and_ring_paths_agree_bitwise(gpu_ctx):
     """Short Remedy-3 lists are bisected by k_rem3_prep itself, long ones by round 1 of the persistent kernel; both
     use the same summation order, so sharding a problem (short lists) must reproduce the unsharded run (long list)."""
