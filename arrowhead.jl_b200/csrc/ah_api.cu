@@ -186,47 +186,47 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
 
     int rc;
     if (hD) {
-    // ---- inputs -> device, padded to whole tiles of the fast kernel's ring.  Pad poles lie strictly
-    // below every real pole (so no shift or bisection point can hit them) and carry weight 0.
-    const int64_t Np = ((N + ah::TILE_POLES - 1) / ah::TILE_POLES) * ah::TILE_POLES;
-    // D | w | w^2 go through one pinned staging block and one copy (pageable sources are staged by the driver in
-    // small pieces: 3 x 256 KB took 50 us + 100 us of host time at n = 32768)
-    if ((size_t)(3 * Np * 8) > ctx->hInCap) {
-        if (ctx->hIn) cudaFreeHost(ctx->hIn);
-        ctx->hIn = nullptr; ctx->hInCap = 0;
-        if (cudaMallocHost((void **)&ctx->hIn, (size_t)(3 * Np * 8)) != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_NOMEM, "cudaMallocHost failed"); }
-        ctx->hInCap = (size_t)(3 * Np * 8);
-    }
-    double *hPadD = ctx->hIn, *hPadW = ctx->hIn + Np, *hPadW2 = ctx->hIn + 2 * Np;
-    std::memcpy(hPadD, hD, N * 8);
-    std::memcpy(hPadW, hW, N * 8);
-    for (int64_t l = 0; l < N; ++l) hPadW2[l] = hW[l] * hW[l];   // one rounding, as z[k]^2 in the reference
-    double pad;
-    if (L.kind == KIND_HALF) {
-        pad = hD[N - 1] / 2.0;
-    } else {
-        double span = hD[0] - hD[N - 1];
-        if (!(span > 0.0)) span = std::max(std::fabs(hD[N - 1]), 1.0);
-        pad = hD[N - 1] - span;
-        if (!std::isfinite(pad)) pad = -1.7976931348623157e308;
-    }
-    for (int64_t l = N; l < Np; ++l) { hPadD[l] = pad; hPadW[l] = 0.0; hPadW2[l] = 0.0; }
-    if ((rc = ensure(ctx, ctx->dD, 3 * Np * 8))) return rc;
-    AH_CUDA(cudaEventRecord(ctx->ev[0], st));
-    AH_CUDA(cudaMemcpyAsync(ctx->dD.p, ctx->hIn, 3 * Np * 8, cudaMemcpyHostToDevice, st));
-    ctx->stats.h2d_bytes += 3 * Np * 8;
-    P.D = (const double *)ctx->dD.p;
-    P.w = P.D + Np;
-    P.w2 = P.D + 2 * Np;
-    P.Np = Np;
-    P.pad = pad;
-    P.z = nullptr;
-    if (hZ) {
-        if ((rc = ensure(ctx, ctx->dZ, N * 8))) return rc;
-        AH_CUDA(cudaMemcpyAsync(ctx->dZ.p, hZ, N * 8, cudaMemcpyHostToDevice, st));
-        ctx->stats.h2d_bytes += N * 8;
-        P.z = (const double *)ctx->dZ.p;
-    }
+        // ---- inputs -> device, padded to whole tiles of the fast kernel's ring.  Pad poles lie strictly
+        // below every real pole (so no shift or bisection point can hit them) and carry weight 0.
+        const int64_t Np = ((N + ah::TILE_POLES - 1) / ah::TILE_POLES) * ah::TILE_POLES;
+        // D | w | w^2 go through one pinned staging block and one copy (pageable sources are staged by the driver in
+        // small pieces: 3 x 256 KB took 50 us + 100 us of host time at n = 32768)
+        if ((size_t)(3 * Np * 8) > ctx->hInCap) {
+            if (ctx->hIn) cudaFreeHost(ctx->hIn);
+            ctx->hIn = nullptr; ctx->hInCap = 0;
+            if (cudaMallocHost((void **)&ctx->hIn, (size_t)(3 * Np * 8)) != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_NOMEM, "cudaMallocHost failed"); }
+            ctx->hInCap = (size_t)(3 * Np * 8);
+        }
+        double *hPadD = ctx->hIn, *hPadW = ctx->hIn + Np, *hPadW2 = ctx->hIn + 2 * Np;
+        std::memcpy(hPadD, hD, N * 8);
+        std::memcpy(hPadW, hW, N * 8);
+        for (int64_t l = 0; l < N; ++l) hPadW2[l] = hW[l] * hW[l];   // one rounding, as z[k]^2 in the reference
+        double pad;
+        if (L.kind == KIND_HALF) {
+            pad = hD[N - 1] / 2.0;
+        } else {
+            double span = hD[0] - hD[N - 1];
+            if (!(span > 0.0)) span = std::max(std::fabs(hD[N - 1]), 1.0);
+            pad = hD[N - 1] - span;
+            if (!std::isfinite(pad)) pad = -1.7976931348623157e308;
+        }
+        for (int64_t l = N; l < Np; ++l) { hPadD[l] = pad; hPadW[l] = 0.0; hPadW2[l] = 0.0; }
+        if ((rc = ensure(ctx, ctx->dD, 3 * Np * 8))) return rc;
+        AH_CUDA(cudaEventRecord(ctx->ev[0], st));
+        AH_CUDA(cudaMemcpyAsync(ctx->dD.p, ctx->hIn, 3 * Np * 8, cudaMemcpyHostToDevice, st));
+        ctx->stats.h2d_bytes += 3 * Np * 8;
+        P.D = (const double *)ctx->dD.p;
+        P.w = P.D + Np;
+        P.w2 = P.D + 2 * Np;
+        P.Np = Np;
+        P.pad = pad;
+        P.z = nullptr;
+        if (hZ) {
+            if ((rc = ensure(ctx, ctx->dZ, N * 8))) return rc;
+            AH_CUDA(cudaMemcpyAsync(ctx->dZ.p, hZ, N * 8, cudaMemcpyHostToDevice, st));
+            ctx->stats.h2d_bytes += N * 8;
+            P.z = (const double *)ctx->dZ.p;
+        }
         ctx->res_valid = true; ctx->res_kind = L.kind; ctx->res_N = L.N; ctx->res_nvec_u = L.nvec_u; ctx->res_nvec_v = L.nvec_v;
         ctx->res_kmax = L.kmax; ctx->res_P = P;
     } else {

@@ -230,7 +230,7 @@ def run_ours(args):
         ms_max, launches_all = ms, launches
     value = n * args.steps / (ms_max * 1e-3)
 
-    # ---- roofline of the dominant kernel (k_fast) on this rank, from the same timed region
+    # ---- roofline of the dominant kernel (k_bisect) on this rank, from the same timed region
     N = n - 1
     fast = res.status == 0            # (k_full's few eigenpairs are included: their first bisection ran in k_bisect)
     n_fast = res.stats["n_fast"]
