@@ -16,11 +16,13 @@
 // pole differences d_l in every sweep.  All scalar state is replicated in registers of every thread
 // and derived only from block-wide all-reductions, so control flow is CTA-uniform.
 #pragma once
+#include "../../include/arrowhead_b200.h"
 #include "ah_device.cuh"
 
 namespace ah {
 
 enum : int { KIND_ARROW = 0, KIND_DPR1 = 1, KIND_HALF = 2 };
+// status word: bits 0..5 = AH_ST_* conditions, bits 8..14 = AH_BR_* branch trace (include/arrowhead_b200.h)
 
 struct Problem {
     int64_t N;         // number of poles
@@ -185,6 +187,7 @@ __device__ void inv_at_value(const Problem &P, double sig, double tol, InvValue 
         rho = __ddiv_rn(-1.0, PQ);
     } else {
         Qout = 1;
+        status |= AH_BR_DD_RHO;
         dd Pd = dd_from(0.0), Qd = dd_from(0.0);
         dd s1 = dd_from(sig);
         for (int64_t l = threadIdx.x; l < N; l += BT) {
@@ -378,6 +381,7 @@ __device__ void solve_full(const Problem &P, const Outputs &O, int64_t k, int64_
         b = __dmul_rn(__dmul_rn(PQ, wz), wz);
     } else if (KIND == KIND_HALF || Kz < 1.0 / (kEps * kEps)) {
         Qout = 1;
+        status |= AH_BR_DD_B;
         dd Pd = dd_from(0.0), Qd = dd_from(0.0);
         const dd s1 = dd_from(sigma);
         for (int64_t l = tid; l < N; l += BT) {
@@ -471,6 +475,7 @@ __device__ void solve_full(const Problem &P, const Outputs &O, int64_t k, int64_
         if (KIND != KIND_HALF) {
             int iter = 0;
             while (Knu > P.tau[2]) {
+                status |= (status & AH_BR_REM3) ? AH_BR_REM3_REPEAT : AH_BR_REM3;
                 nu = sideR ? fabs(nu) : -fabs(nu);
                 nu1 = -sign_jl(nu) * nu1;
                 double sigma1 = __dadd_rn(__ddiv_rn(__dadd_rn(nu1, nu), __dmul_rn(__dmul_rn(2.0, nu), nu1)), sigma);
@@ -479,8 +484,10 @@ __device__ void solve_full(const Problem &P, const Outputs &O, int64_t k, int64_
                 inv_at_value<KIND, BT>(P, sigma1, P.tau[3], R, status, red);
                 Krho = R.Krho;
                 nu = bisect_dpr1_dev<KIND, BT>(P, sigma1, R, sideR, steps, red);
-                if (KIND == KIND_ARROW && sideR && D[0] > 0.0 && nu < 0.0)
+                if (KIND == KIND_ARROW && sideR && D[0] > 0.0 && nu < 0.0) {
+                    status |= AH_BR_RL_RETRY;
                     nu = bisect_dpr1_dev<KIND, BT>(P, sigma1, R, false, steps, red);
+                }
                 nu1 = __dadd_rn(R.maxabsD, __dmul_rn(fabs(R.rho), R.uu));
                 Knu = __ddiv_rn(nu1, fabs(nu));
                 sigma = sigma1;
@@ -496,6 +503,7 @@ __device__ void solve_full(const Problem &P, const Outputs &O, int64_t k, int64_
                 mu = __ddiv_rn(1.0, nu);
                 lam2 = __dadd_rn(mu, __dmul_rn(sigma, sigma));
             } else {
+                status |= AH_BR_REM3;
                 nu = sideR ? fabs(nu) : -fabs(nu);
                 nu1 = -sign_jl(nu) * nu1;
                 double sigma1 = __dadd_rn(__ddiv_rn(__dadd_rn(nu1, nu), __dmul_rn(__dmul_rn(2.0, nu), nu1)),
@@ -573,10 +581,12 @@ __device__ void solve_full(const Problem &P, const Outputs &O, int64_t k, int64_
         if (rem1) {
             InvValue R;
             inv_at_value<KIND, BT>(P, 0.0, P.tau[3], R, status, red);
+            status |= AH_BR_REM1;
             Krho = R.Krho;
             if (KIND == KIND_HALF) { if (Qout == 1) Qout += 4; }
             else Qout += 4 * R.Qout;
             if (isinf(R.rho)) {
+                status |= AH_BR_REM1_ZERO;
                 lambda = 0.0;
             } else {
                 double s1 = 0.0, s2 = 0.0;

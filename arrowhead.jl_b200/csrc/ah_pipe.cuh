@@ -432,7 +432,7 @@ __device__ __forceinline__ void bisect_finalize(const Problem &P, const Outputs 
             O.kb[col] = S.Kb; O.kz[col] = S.Kz; O.knu[col] = Knu; O.krho[col] = (ROUND == 0) ? 0.0 : S.krho;
             O.qout[col] = 0;
             O.steps[col] = S.steps;
-            O.status[col] = 0;
+            O.status[col] = (ROUND == 0) ? 0 : AH_BR_REM3;   // round 1 = one plain Remedy-3 re-shift (anything more went to k_full)
         }
     }
 }

@@ -265,7 +265,7 @@ __device__ void solve_roots(const Problem &P, const double *__restrict__ Wlo, do
         O.kb[col] = Kb; O.kz[col] = Kz; O.knu[col] = Knu; O.krho[col] = Krho;
         O.qout[col] = Qout;
         O.steps[col] = steps;
-        O.status[col] = status;
+        O.status[col] = status & AH_ST_MASK;   // rootsah keeps no branch trace (its per-k solver differs, arrowhead7.jl:351-495)
     }
 }
 

@@ -55,6 +55,18 @@ extern "C" {
                                      accuracy here (first-stage K_nu ~ 1/eps, Remedy 3 re-shifted past the eigenvalue);
                                      the reference returns such values silently -- redo this k in higher precision */
 
+/* Branch trace, bits 8..14 of the same status word (informational: `status & 0xff` are the conditions above).
+ * Which non-standard branches of the reference's per-k solver the eigenpair went through; the CPU oracle sets the
+ * same bits, so the parity tests compare the branch taken for every eigenpair, not only the results. */
+#define AH_BR_DD_B 0x100          /* b recomputed in Dekker double-double (inv!: Kb/Kz test failed, arrowhead3.jl:191-230) */
+#define AH_BR_REM3 0x200          /* Remedy 3: re-shift between the poles (K_nu > tolnu, arrowhead3.jl:466-513) */
+#define AH_BR_REM3_REPEAT 0x400   /* ... more than once (the `while Knu > tau[3]` loop went round again) */
+#define AH_BR_RL_RETRY 0x800      /* 'R' -> 'L' retry of the DPR1 bisection (arrowhead3.jl:499-501) */
+#define AH_BR_DD_RHO 0x1000       /* rho of an inverse at a non-pole shift in double-double (K_rho >= tolrho, :292-321) */
+#define AH_BR_REM1 0x2000         /* Remedy 1: Rayleigh quotient with the inverse of the unshifted matrix (:526-544) */
+#define AH_BR_REM1_ZERO 0x4000    /* ... whose rho is infinite: lambda = 0 (:538-539) */
+#define AH_ST_MASK 0xff           /* status & AH_ST_MASK == 0: the eigenpair is complete and as the reference returns it */
+
 /* where an eigenvector buffer lives */
 #define AH_MEM_HOST 0
 #define AH_MEM_DEVICE 1

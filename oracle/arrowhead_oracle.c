@@ -61,6 +61,15 @@ typedef double acc_t;
 #define AH_ST_NEEDS_BIGFLOAT 2  /* reference would switch to BigFloat (Qout 50 / 100) */
 #define AH_ST_POLE_RETURN 4     /* "came back with a pole" sub-path (throws in the reference) */
 #define AH_ST_REF_THROWS 8      /* reference raises (e.g. arrowhead4.jl:324 undefined `sigma`) */
+/* branch trace (bits 8..14 of the status word; same meaning as AH_BR_* in include/arrowhead_b200.h): which
+ * non-standard branches of the reference's per-k solver this eigenpair went through */
+#define AH_BR_DD_B 0x100        /* b recomputed in double-double (inv!, Kb/Kz test failed) */
+#define AH_BR_REM3 0x200        /* Remedy 3: re-shift between the poles (K_nu > tolnu) */
+#define AH_BR_REM3_REPEAT 0x400 /* ... more than once (the while loop of arrowhead3.jl:466 went round again) */
+#define AH_BR_RL_RETRY 0x800    /* 'R' -> 'L' retry of the DPR1 bisection (arrowhead3.jl:499-501) */
+#define AH_BR_DD_RHO 0x1000     /* rho of an inverse at a non-pole shift in double-double (K_rho >= tolrho) */
+#define AH_BR_REM1 0x2000       /* Remedy 1: Rayleigh quotient on the inverse of the unshifted matrix */
+#define AH_BR_REM1_ZERO 0x4000  /* ... whose rho is infinite: lambda = 0 */
 
 /* ------------------------------------------------------------------ Julia scalar semantics */
 static inline double jl_max(double a, double b) {
@@ -392,6 +401,7 @@ static void symarrow_k(int64_t N, const double *D, const double *z, double a, in
 
     double b;
     arrow_inv_shift_index(N, D, z, a, i, tau[0], tau[1], s->bd, s->bz, &b, &Kb, &Kz, &Qout, &status);
+    if (Qout == 1) status |= AH_BR_DD_B;
     double nu = bisect_arrow(s->bd, s->bz, b, N, side, s->w, &steps);
 
     if (isinf(nu)) {
@@ -405,6 +415,7 @@ static void symarrow_k(int64_t N, const double *D, const double *z, double a, in
         nu1 = jl_max(jl_pairwise_sum(s->t, 0, N - 1) + fabs(b), nu1);
         Knu = nu1 / fabs(nu);
         while (Knu > tau[2]) {
+            status |= (status & AH_BR_REM3) ? AH_BR_REM3_REPEAT : AH_BR_REM3;
             nu = side == 'R' ? fabs(nu) : -fabs(nu);
             nu1 = -jl_sign(nu) * nu1;
             double sigma1 = (nu1 + nu) / (2.0 * nu * nu1) + sigma;
@@ -418,9 +429,12 @@ static void symarrow_k(int64_t N, const double *D, const double *z, double a, in
             int64_t Qout1 = 0;
             double rho;
             arrow_inv_shift_value(N, D, z, a, sigma1, tau[3], s->d1, s->u1, &rho, &Krho, &Qout1, &status);
+            if (Qout1 != 0) status |= AH_BR_DD_RHO;
             nu = bisect_dpr1(s->d1, s->u1, rho, N + 1, side, s->w, &steps);
-            if (side == 'R' && D[0] > 0.0 && nu < 0.0)
+            if (side == 'R' && D[0] > 0.0 && nu < 0.0) {
+                status |= AH_BR_RL_RETRY;
                 nu = bisect_dpr1(s->d1, s->u1, rho, N + 1, 'L', s->w, &steps);
+            }
             double mD = fabs(s->d1[0]);
             for (int64_t l = 1; l <= N; ++l) mD = jl_max(mD, fabs(s->d1[l]));
             acc_t uu = 0.0;
@@ -449,8 +463,11 @@ static void symarrow_k(int64_t N, const double *D, const double *z, double a, in
                 int64_t Qout1 = 0;
                 double rho;
                 arrow_inv_shift_value(N, D, z, a, 0.0, tau[3], s->d1, s->u1, &rho, &Krho, &Qout1, &status);
+                status |= AH_BR_REM1;
+                if (Qout1 != 0) status |= AH_BR_DD_RHO;
                 Qout = Qout + 4 * Qout1;
                 if (isinf(rho)) {
+                    status |= AH_BR_REM1_ZERO;
                     lambda = 0.0;
                 } else {
                     for (int64_t l = 0; l < n; ++l) s->t[l] = v[l] * v[l] * s->d1[l];
@@ -776,6 +793,7 @@ static void symdpr1_k(int64_t n, const double *D, const double *u, double r, int
     }
     double b;
     dpr1_inv_shift_index(n, D, u, r, i, tau[0], tau[1], s->bd, s->bz, &b, &Kb, &Kz, &Qout, &status, s->t);
+    if (Qout == 1) status |= AH_BR_DD_B;
     double nu = bisect_arrow(s->bd, s->bz, b, n - 1, side, s->w, &steps);
 
     if (isinf(nu)) {
@@ -789,6 +807,7 @@ static void symdpr1_k(int64_t n, const double *D, const double *u, double r, int
         nu1 = jl_max(jl_pairwise_sum(s->t, 0, n - 2) + fabs(b), nu1);
         Knu = nu1 / fabs(nu);
         while (Knu > tau[2]) {
+            status |= (status & AH_BR_REM3) ? AH_BR_REM3_REPEAT : AH_BR_REM3;
             nu = side == 'R' ? fabs(nu) : -fabs(nu);
             nu1 = -jl_sign(nu) * nu1;
             double sigma1 = (nu1 + nu) / (2.0 * nu * nu1) + sigma;
@@ -798,6 +817,7 @@ static void symdpr1_k(int64_t n, const double *D, const double *u, double r, int
             int64_t Qout1 = 0;
             double rho;
             dpr1_inv_shift_value(n, D, u, r, sigma1, tau[3], s->d1, s->u1, &rho, &Krho, &Qout1, &status);
+            if (Qout1 != 0) status |= AH_BR_DD_RHO;
             nu = bisect_dpr1(s->d1, s->u1, rho, n, side, s->w, &steps);
             double mD = fabs(s->d1[0]);
             for (int64_t l = 1; l < n; ++l) mD = jl_max(mD, fabs(s->d1[l]));
@@ -826,8 +846,11 @@ static void symdpr1_k(int64_t n, const double *D, const double *u, double r, int
                 int64_t Qout1 = 0;
                 double rho;
                 dpr1_inv_shift_value(n, D, u, r, 0.0, tau[3], s->d1, s->u1, &rho, &Krho, &Qout1, &status);
+                status |= AH_BR_REM1;
+                if (Qout1 != 0) status |= AH_BR_DD_RHO;
                 Qout = Qout + 4 * Qout1;
                 if (isinf(rho)) {
+                    status |= AH_BR_REM1_ZERO;
                     lambda = 0.0;
                 } else {
                     for (int64_t l = 0; l < n; ++l) s->t[l] = v[l] * v[l] * s->d1[l];
@@ -983,6 +1006,7 @@ static void halfarrow_k(int64_t nd, int64_t nz, const double *D, const double *z
     }
     double b;
     half_inv_shift_index(nd, nz, D, z, z1, i, tau[0], tau[1], s->bd, s->bz, &b, &Kb, &Kz, &Qout);
+    if (Qout == 1) status |= AH_BR_DD_B;
     /* the reference's scratch arrow has one extra never-written slot in the tip shape
        (arrowhead6.jl:636 vs :206-207); it reads as zero in fresh memory and contributes nothing */
     double nu = bisect_arrow(s->bd, s->bz, b, nd, side, s->w, &steps);
@@ -1005,6 +1029,7 @@ static void halfarrow_k(int64_t nd, int64_t nz, const double *D, const double *z
             sig_v = sigma;
             lam2 = mu_v + sigma * sigma;
         } else {
+            status |= AH_BR_REM3;
             nu = side == 'R' ? fabs(nu) : -fabs(nu);
             nu1 = -jl_sign(nu) * nu1;
             double sigma1 = (nu1 + nu) / (2.0 * nu * nu1) + sigma * sigma;
@@ -1019,6 +1044,7 @@ static void halfarrow_k(int64_t nd, int64_t nz, const double *D, const double *z
                 int64_t Qout1 = 0;
                 double rho;
                 half_inv_shift_value(nd, nz, D, z, z1, ss1, tau[3], s->d1, s->u1, &rho, &Krho, &Qout1);
+                if (Qout1 != 0) status |= AH_BR_DD_RHO;
                 double nu1b = bisect_dpr1(s->d1, s->u1, rho, nd + 1, side, s->w, &steps);
                 mu_v = 1.0 / nu1b;
                 sig_v = ss1;
@@ -1041,8 +1067,11 @@ static void halfarrow_k(int64_t nd, int64_t nz, const double *D, const double *z
             int64_t Qout1 = 0;
             double rho;
             half_inv_shift_value(nd, nz, D, z, z1, 0.0, tau[3], s->d1, s->u1, &rho, &Krho, &Qout1);
+            status |= AH_BR_REM1;
+            if (Qout1 != 0) status |= AH_BR_DD_RHO;
             if (Qout == 1) Qout = Qout + 4;
             if (isinf(rho)) {
+                status |= AH_BR_REM1_ZERO;
                 lambda = 0.0;
             } else {
                 for (int64_t l = 0; l < n; ++l) s->t[l] = v[l] * v[l] * s->d1[l];

@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Small inputs that drive the per-k solver through every non-standard branch ("k_full's rare branches
+have no hit-count assertion"): double-double b, Remedy 3, repeated Remedy 3, the 'R'->'L' retry, double-double rho,
+Remedy 1, Remedy 1 with rho = Inf (lambda = 0), |nu| = Inf.
+
+The reference's own tests pin none of these except Remedy 3 and double-double b, so the cases
+are FOUND here by a seeded random search that asks the CPU oracle (oracle/arrowhead_oracle.c, which records the branch
+taken in bits 8..14 of its status word) which branch an input takes.  The inputs are stored exactly (hex floats) in
+tests/golden/branch_cases.json together with the oracle's status words; tests/test_branches.py re-runs the oracle on
+them (CPU) and requires the CUDA path to take the same branch for every eigenpair (GPU).
+
+    python tests/golden/make_branch_cases.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import oracle  # noqa: E402
+
+BITS = {"DD_B": 0x100, "REM3": 0x200, "REM3_REPEAT": 0x400, "RL_RETRY": 0x800, "DD_RHO": 0x1000, "REM1": 0x2000,
+        "REM1_ZERO": 0x4000, "NU_INF": 0x1}
+TARGETS = {
+    "symarrow": ["DD_B", "REM3", "REM3_REPEAT", "RL_RETRY", "DD_RHO", "REM1", "REM1_ZERO", "NU_INF"],
+    "symdpr1": ["DD_B", "REM3", "REM3_REPEAT", "DD_RHO", "REM1", "NU_INF"],
+    "halfarrow": ["DD_B", "REM3", "DD_RHO", "REM1", "NU_INF"],
+}
+
+
+def hexv(x):
+    return [float(v).hex() for v in np.atleast_1d(x)]
+
+
+def run(lib, kind, D, w, top):
+    N = D.size
+    tau = oracle.default_tau(N)
+    if kind == "symarrow":
+        return lib.symarrow(D, w, top, tau, vectors=False)
+    if kind == "symdpr1":
+        return lib.symdpr1(D, w, top, tau, vectors=False)
+    return lib.halfarrow(D, w, tau, vectors=False)
+
+
+def candidates(rng):
+    """(kind, D, w, top) stream: graded / dyadic / integer / tiny / singular families, N = 2..13"""
+    fixed = [
+        ("symarrow", np.array([1.0, -1.0]), np.array([1.0, 1.0]), 0.0),                 # exactly singular: Remedy 1, rho = Inf
+        ("symdpr1", np.array([2.0, 1.0, -0.5]), np.array([1e-3, 1.0, 1.0]), 1.0),
+    ]
+    for c in fixed:
+        yield c
+    while True:
+        N = int(rng.integers(2, 14))
+        mode = int(rng.integers(0, 8))
+        sgn = np.where(rng.random(N) < 0.5, -1.0, 1.0)
+        if mode == 0:
+            D = np.exp(rng.uniform(-30, 5, N)) * sgn; w = np.exp(rng.uniform(-20, 5, N)); top = float(np.exp(rng.uniform(-20, 5)) * rng.choice([-1, 1]))
+        elif mode == 1:
+            D = 2.0 ** (-rng.integers(0, 60, N).astype(float)) * np.where(rng.random(N) < 0.3, -1.0, 1.0); w = rng.random(N); top = 0.0
+        elif mode == 2:
+            D = rng.integers(-3, 4, N).astype(float) + rng.random(N) * 1e-8; w = rng.integers(1, 3, N).astype(float); top = float(rng.integers(-2, 3))
+        elif mode == 3:
+            D = rng.random(N) * 10.0 ** rng.integers(-18, 1, N); w = rng.random(N) * 10.0 ** rng.integers(-10, 1, N); top = float(rng.random() * 10.0 ** rng.integers(-18, 1))
+        elif mode == 4:
+            D = np.concatenate([[1.0], -(rng.random(N - 1) + 1e-3)]); w = rng.random(N) * 10.0 ** rng.integers(-8, 1, N); top = float(-rng.random())
+        elif mode == 5:
+            D = rng.random(N) - 0.5; w = rng.random(N); top = float((w * w / D).sum())                     # Schur complement 0
+        elif mode == 6:
+            D = rng.random(N); w = 1e-170 * (0.5 + rng.random(N)); top = float(rng.random())               # 1/z^2 overflows
+        else:
+            D = np.exp(20 * (rng.random(N) - 0.5)) * sgn; w = np.exp(20 * (rng.random(N) - 0.5)); top = float(np.exp(20 * (rng.random() - 0.5)))
+        D = np.sort(D)[::-1].copy()
+        if np.any(np.diff(D) >= 0) or np.any(w == 0) or np.any(D == 0) or not np.all(np.isfinite(D)):
+            continue
+        yield "symarrow", D, w, top
+        rho = abs(top) + 10.0 ** int(rng.integers(-10, 2))
+        yield "symdpr1", D, w, rho
+        Dh = np.sort(np.abs(D))[::-1].copy()
+        if np.all(np.diff(Dh) < 0):
+            tip = float(rng.random() * 10.0 ** int(rng.integers(-12, 1)))
+            yield "halfarrow", Dh, np.concatenate([w, [tip]]), None
+            yield "halfarrow", Dh, w, None
+
+
+def main():
+    lib = oracle.get_lib()
+    rng = np.random.default_rng(20261020)
+    need = {(kind, t) for kind, ts in TARGETS.items() for t in ts}
+    cases = []
+    tried = 0
+    for kind, D, w, top in candidates(rng):
+        tried += 1
+        if tried > 400000 or not need:
+            break
+        O = run(lib, kind, D, w, top)
+        hit = [t for t in TARGETS[kind] if (kind, t) in need and ((O.status & BITS[t]) != 0).any()]
+        if not hit:
+            continue
+        for t in hit:
+            need.discard((kind, t))
+        cases.append({"kind": kind, "fires": hit, "D": hexv(D), "w": hexv(w), "top": None if top is None else float(top).hex(),
+                      "status": [int(s) for s in O.status], "qout": [int(q) for q in O.qout]})
+        print(f"case {len(cases):2d} ({tried} tried): {kind} N={D.size} fires {hit}", flush=True)
+    if need:
+        print("NOT FOUND:", sorted(need))
+    with open(os.path.join(HERE, "branch_cases.json"), "w", encoding="utf-8") as f:
+        json.dump({"bits": BITS, "not_found": sorted(list(x) for x in need), "cases": cases}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

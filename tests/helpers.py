@@ -48,7 +48,30 @@ def shift_margin_symdpr1(D, u, rho, k):
     return float(abs(F) / (np.abs(t).sum() + 1))
 
 
-def compare_range(gpu, orc, hi=None, *, lam_tol=10.0, vec_tol=100.0, k_tol=1e-9, margin_fn=None):
+def shift_margin_halfarrow(D, z, k):
+    """the same for svd(::HalfArrow): Fmiddle of arrowhead6.jl:379-383 on the squared poles, in long double."""
+    Dl = D.astype(np.longdouble); zl = z.astype(np.longdouble)
+    nd = D.size
+    Dk = Dl[k - 1]
+    Dtemp = (Dl - Dk) * (Dl + Dk)
+    atemp = (zl * zl).sum() - Dk * Dk
+    mid = Dtemp[k - 2] / 2
+    z1 = zl[:nd] * Dl
+    t = z1 * z1 / (Dtemp - mid)
+    F = (atemp - mid) - t.sum()
+    return float(abs(F) / (np.abs(t).sum() + abs(atemp - mid)))
+
+
+def interlaces(poles, kmax, k, lam):
+    """Cauchy interlacing of eigenvalue k (1-based, descending) with the descending poles; independent of any library."""
+    N = poles.size
+    hi_ok = True if k == 1 else lam <= poles[k - 2]
+    lo_ok = True if k > N else lam >= poles[k - 1]
+    return bool(hi_ok and lo_ok)
+
+
+def compare_range(gpu, orc, hi=None, *, lam_tol=10.0, vec_tol=100.0, k_tol=1e-9, margin_fn=None, max_excluded=None,
+                  poles=None):
     """GPU k-range result vs the oracle's (same k-range).  Returns a dict of the measured maxima.
 
     Bars (BASELINE.json north_star): shift index / Qout / status exact; eigenvalues <= 10 eps relative;
@@ -62,7 +85,14 @@ def compare_range(gpu, orc, hi=None, *, lam_tol=10.0, vec_tol=100.0, k_tol=1e-9,
         (a) 3 x the reference's own summation noise |oracle - oracle_hi| of that eigenpair, and
         (b) Knu x [0.1 eps (eigenvalue) | 1 eps (vector entries)]: a one-ulp change of a secular term
             moves nu by about Knu ulps (seen already at n = 10, where no summation noise exists).
-    `hi=None` disables (a)."""
+    `hi=None` disables (a).
+
+    Eigenpairs are EXCLUDED from the value comparison only when (1) the shift index differs AND margin_fn proves the
+    reference's own sign test is within rounding of zero there, (2) oracle and oracle_hi disagree on the shift,
+    (3) the library flags AH_ST_INTERLACE -- and, when `poles` is given, that flag is verified here: the GPU's or the
+    oracle's value must really violate the interlacing bounds (or be NaN), a spurious flag fails --, (4) the oracle's
+    value is NaN.  At most `max_excluded` eigenpairs may be excluded (default max(2, cnt/1000)); tests on the
+    benchmark distributions pass 0."""
     cnt = gpu.lam.size
     assert cnt == orc.lam.size
     same_shift = gpu.sind == orc.sind
@@ -77,6 +107,13 @@ def compare_range(gpu, orc, hi=None, *, lam_tol=10.0, vec_tol=100.0, k_tol=1e-9,
         ok &= hi.sind == orc.sind
     # AH_ST_INTERLACE (32) is a diagnostic of this library only (the reference has no such test): eigenpairs it marks
     # are the ones where the reference's own answer is rounding noise, so they are excluded from the value comparison
+    flagged = np.flatnonzero((gpu.status & 32) != 0)
+    if poles is not None:
+        for c in flagged:
+            k = gpu.k0 + int(c)
+            gl, ol = float(gpu.lam[c]), float(orc.lam[c])
+            assert (np.isnan(gl) or np.isnan(ol) or not interlaces(poles, cnt, k, gl) or not interlaces(poles, cnt, k, ol)), \
+                f"AH_ST_INTERLACE set at k={k} although {gl!r} (oracle {ol!r}) interlaces"
     ok &= (gpu.status & 32) == 0
     # ... and where the oracle itself returns NaN (e.g. sqrt of a rounding-negative mu + sigma^2 in arrowhead6.jl:420:
     # the reference's value is NaN or 8 digits depending on which way the noise falls) the GPU must say so
@@ -84,9 +121,23 @@ def compare_range(gpu, orc, hi=None, *, lam_tol=10.0, vec_tol=100.0, k_tol=1e-9,
     assert np.all(np.isnan(gpu.lam[ref_nan]) | ((gpu.status[ref_nan] & 32) != 0) | (gpu.krho[ref_nan] != 0)), \
         "oracle NaN, GPU finite and unflagged"
     ok &= ~ref_nan
+    cap = max(2, cnt // 1000) if max_excluded is None else max_excluded
+    assert int((~ok).sum()) <= cap, f"{int((~ok).sum())} of {cnt} eigenpairs excluded from the comparison (cap {cap}): " \
+                                    f"shift {int(bad.size)}, flagged {int(flagged.size)}, oracle NaN {int(ref_nan.sum())}"
     assert np.array_equal(gpu.qout[ok], orc.qout[ok]), "Qout differs"
-    assert np.array_equal(gpu.status[ok], orc.status[ok]), "status differs"
-    out = {"n_shift_ambiguous": int(bad.size), "n": int(cnt), "n_interlace_flagged": int(((gpu.status & 32) != 0).sum())}
+    # status = conditions (bits 0..5) + branch trace (bits 8..14: which Remedy / double-double branch was taken).
+    # Everything must equal the oracle's, eigenpair by eigenpair; only "Remedy 3 once more" and the 'R'->'L' retry
+    # are decided by a K_nu / sign that is itself rounding noise after a first re-shift, so those two bits may differ
+    # on a few eigenpairs that did take a Remedy (counted, capped).
+    noisy_bits = 0x400 | 0x800
+    gs, os_ = gpu.status[ok], orc.status[ok]
+    assert np.array_equal(gs & ~noisy_bits, os_ & ~noisy_bits), \
+        f"status / branch trace differs at k={gpu.k0 + np.flatnonzero(ok)[np.flatnonzero((gs ^ os_) & ~noisy_bits)][:8]}"
+    nb = ((gs ^ os_) & noisy_bits) != 0
+    assert np.all(orc.krho[ok][nb] != 0), "repeat / retry branch differs on an eigenpair that took no Remedy"
+    assert int(nb.sum()) <= max(1, int(0.05 * (orc.krho[ok] != 0).sum())), f"{int(nb.sum())} repeat/retry branch decisions differ"
+    out = {"n_shift_ambiguous": int(bad.size), "n": int(cnt), "n_interlace_flagged": int(((gpu.status & 32) != 0).sum()),
+           "n_excluded": int((~ok).sum()), "n_branch_noise": int(nb.sum())}
     knu = np.where(np.isfinite(orc.knu), orc.knu, 0.0)
     den = np.abs(orc.lam)
     den[den == 0] = 1.0

@@ -30,14 +30,14 @@ def test_structured_families_match_the_oracle(gpu_ctx, oracle_lib, oracle_hi, N)
         tau = oracle.default_tau(N)
         G = gpu_ctx.symarrow(D, z, a)
         compare_range(G, oracle_lib.symarrow(D, z, a, tau), oracle_hi.symarrow(D, z, a, tau),
-                      margin_fn=lambda k: shift_margin_symarrow(D, z, a, k))
+                      margin_fn=lambda k: shift_margin_symarrow(D, z, a, k), max_excluded=max(2, N // 20), poles=D)
         flagged = (G.status & ab.ST_INTERLACE) != 0                                       # never silent: in bounds, or flagged
         assert np.all((G.lam[1:] <= D) | flagged[1:]) and np.all((G.lam[:-1] >= D) | flagged[:-1]), name
         assert flagged.sum() <= 1, name
         rho = abs(a) + 0.1
         G = gpu_ctx.symdpr1(D, z, rho)
         compare_range(G, oracle_lib.symdpr1(D, z, rho, tau), oracle_hi.symdpr1(D, z, rho, tau),
-                      margin_fn=lambda k: shift_margin_symdpr1(D, z, rho, k))
+                      margin_fn=lambda k: shift_margin_symdpr1(D, z, rho, k), max_excluded=max(2, N // 20))
         flagged = (G.status & ab.ST_INTERLACE) != 0
         assert np.all((G.lam >= D) | flagged) and np.all((G.lam[1:] <= D[:-1]) | flagged[1:]), name
         seen += 1
