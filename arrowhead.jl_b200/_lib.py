@@ -326,6 +326,10 @@ class Context:
     def memcpy_d2h(self, dst: np.ndarray, src_dev, nbytes):
         self._check(self.lib.ah_memcpy_d2h(self.handle, dst.ctypes.data_as(C.c_void_p), C.c_void_p(int(src_dev)), nbytes))
 
+    def memcpy_h2d(self, dst_dev, src: np.ndarray, nbytes):
+        src = np.ascontiguousarray(src)
+        self._check(self.lib.ah_memcpy_h2d(self.handle, C.c_void_p(int(dst_dev)), src.ctypes.data_as(C.c_void_p), nbytes))
+
     def pinned_alloc(self, nbytes) -> int:
         p = C.c_void_p()
         self._check(self.lib.ah_host_alloc_pinned(self.handle, C.byref(p), nbytes))

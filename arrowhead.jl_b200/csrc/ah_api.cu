@@ -64,7 +64,8 @@ struct ah_ctx {
     cublasHandle_t blas = nullptr;       // created on first use (ah_dgemm_batched)
     DevBuf dPtrA, dPtrB, dPtrC, dIdx, dBatchA;
     std::vector<cudaEvent_t> chunk_ev;   // 5 timing events per column block of the current call
-    unsigned long long *hCounts = nullptr;  // pinned, 64 entries: per-block hand-over counts of the last call
+    unsigned long long *hCounts = nullptr;  // pinned, 2 per column block: hand-over / Remedy-3 counts of the last call
+    size_t hCountsCap = 0;
 };
 
 namespace {
@@ -183,6 +184,19 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         return fail(ctx, AH_ERR_INVALID_ARG, "rowmap needs device-resident U/V (ah_set_identity + AH_MEM_DEVICE)");
     if (out->U && out->ldu < (out->rowmap_u ? 1 : L.nvec_u)) return fail(ctx, AH_ERR_INVALID_ARG, "ldu too small");
     if (L.kind == KIND_HALF && out->V && out->ldv < (out->rowmap_v ? 1 : L.nvec_v)) return fail(ctx, AH_ERR_INVALID_ARG, "ldv too small");
+    // Mapped stores (`U[zx,zx[k]] = v`): entry r of vector k goes to row rowmap[r] of COLUMN rowmap_u[k-1].  The column
+    // index of V is taken from rowmap_u as well (`V[zxv,zx[k]] = v`, arrowhead6.jl:640), so a HalfArrow call maps
+    // both factors or neither; every index must lie inside the leading dimension.
+    if (L.kind == KIND_HALF && out->V && out->U && ((out->rowmap_u != nullptr) != (out->rowmap_v != nullptr)))
+        return fail(ctx, AH_ERR_INVALID_ARG, "HalfArrow: rowmap_u and rowmap_v must be given together");
+    if (L.kind == KIND_HALF && out->rowmap_v && !out->rowmap_u) return fail(ctx, AH_ERR_INVALID_ARG, "HalfArrow: rowmap_v needs rowmap_u (it supplies the column index)");
+    if (out->rowmap_u && k1 > L.nvec_u) return fail(ctx, AH_ERR_INVALID_ARG, "rowmap_u has no entry for every k of the range");
+    if (out->rowmap_u && out->U)
+        for (int64_t r = 0; r < L.nvec_u; ++r)
+            if (out->rowmap_u[r] < 0 || out->rowmap_u[r] >= out->ldu) return fail(ctx, AH_ERR_INVALID_ARG, "rowmap_u entry outside [0, ldu)");
+    if (L.kind == KIND_HALF && out->rowmap_v && out->V)
+        for (int64_t r = 0; r < L.nvec_v; ++r)
+            if (out->rowmap_v[r] < 0 || out->rowmap_v[r] >= out->ldv) return fail(ctx, AH_ERR_INVALID_ARG, "rowmap_v entry outside [0, ldv)");
 
     int rc;
     if (hD) {
@@ -300,10 +314,17 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     float ms_main = 0.f, ms_all = 0.f;
     int64_t n_full = 0;
     int nbuf = 0, n_count_reads = 0;
-    for (int q = 0; q < 64; ++q) ctx->hCounts[q] = 0;
     // host-staged: a short first block gets the copy engine going early (the copies, not the kernels, bound this path)
     const int64_t first = (staged && chunk < cnt) ? std::min<int64_t>(chunk, 1024) : chunk;
     const int nchunks = (int)(1 + (cnt > first ? (cnt - first + chunk - 1) / chunk : 0));
+    if ((size_t)(2 * nchunks) > ctx->hCountsCap) {   // per-block hand-over / Remedy-3 counts of this call (pinned)
+        if (ctx->hCounts) cudaFreeHost(ctx->hCounts);
+        ctx->hCounts = nullptr; ctx->hCountsCap = 0;
+        const size_t want = std::max<size_t>(64, 2 * (size_t)nchunks);
+        if (cudaMallocHost((void **)&ctx->hCounts, want * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_NOMEM, "cudaMallocHost failed"); }
+        ctx->hCountsCap = want;
+    }
+    for (int q = 0; q < 2 * nchunks; ++q) ctx->hCounts[q] = 0;
     while ((int)ctx->chunk_ev.size() < 5 * nchunks) {
         cudaEvent_t e;
         AH_CUDA(cudaEventCreate(&e));
@@ -332,7 +353,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             else { Oc.V = wantV ? out->V + c0 * out->ldv : nullptr; Oc.ldv = out->ldv; }
         } else {
             Oc.U = wantU ? out->U + (out->rowmap_u ? 0 : c0 * out->ldu) : nullptr; Oc.ldu = out->ldu;
-            Oc.V = wantV ? out->V + (out->rowmap_u ? 0 : c0 * out->ldv) : nullptr; Oc.ldv = out->ldv;
+            Oc.V = wantV ? out->V + (out->rowmap_u ? 0 : c0 * out->ldv) : nullptr; Oc.ldv = out->ldv;   // (column index: rowmap_u, see above)
         }
         const int64_t kb = k0 + c0;
         int64_t *dlist = (int64_t *)ctx->dList.p;
@@ -398,9 +419,9 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                 AH_CUDA(cudaGetLastError());
                 ctx->stats.launches += 1;
             }
-            AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (nbuf & 31)], dcount, 8, cudaMemcpyDeviceToHost, st));
-            AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (nbuf & 31) + 1], dcount + 2, 8, cudaMemcpyDeviceToHost, st));
-            n_count_reads = std::min(nbuf + 1, 32);
+            AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (size_t)nbuf], dcount, 8, cudaMemcpyDeviceToHost, st));
+            AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (size_t)nbuf + 1], dcount + 2, 8, cudaMemcpyDeviceToHost, st));
+            n_count_reads = nbuf + 1;
             AH_CUDA(cudaEventRecord(E[4], st));
         } else {
             AH_CUDA(cudaEventRecord(E[3], st));
@@ -665,7 +686,7 @@ int ah_create(ah_ctx **pctx, int device) {
     }
     for (auto &ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     for (auto &ev : ctx->ev_stage) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
-    if (ok) ok = cudaMallocHost((void **)&ctx->hCounts, 64 * sizeof(unsigned long long)) == cudaSuccess;
+    if (ok) { ok = cudaMallocHost((void **)&ctx->hCounts, 64 * sizeof(unsigned long long)) == cudaSuccess; if (ok) ctx->hCountsCap = 64; }
     if (ok) ok = ah::configure_pipe_kernels() == 0;
     if (!ok) {
         cudaError_t le = cudaGetLastError();

@@ -166,4 +166,13 @@ __device__ __forceinline__ double secular_term_acc(double acc, double d, double 
     return __fma_rn(w2, rcp_fast(t), acc);
 }
 
+// The same term with IEEE divisions only: w2/(d*(1-m*d)) is +-Inf when the bisection point sits exactly on an inverse
+// pole (as z'^2/(D'-m) is in the reference) and 0 when the denominator overflows, where the reciprocal-seed version
+// above produces NaN (0*Inf inside the correction).  Used to redo a sweep whose sum came out NaN.
+__device__ __forceinline__ double secular_term_exact(double d, double m, double w2) {
+    if (w2 == 0.0) return 0.0;
+    double e = __fma_rn(-m, d, 1.0);
+    return __ddiv_rn(w2, __dmul_rn(d, e));
+}
+
 }  // namespace ah

@@ -269,6 +269,14 @@ __device__ double bisect_dpr1_dev(const Problem &P, double sig, const InvValue &
             acc = secular_term_acc(acc, dshift<KIND>(D[l], sig), middle, __dmul_rn(w, w));
         }
         double S = block_allreduce(acc, OpSum(), red);
+        if (S != S) {   // NaN from the reciprocal-seed term (bisection point on an inverse pole, overflow): exact divisions
+            acc = 0.0;
+            for (int64_t l = threadIdx.x; l < N; l += BT) {
+                double w = W[l];
+                acc = __dadd_rn(acc, secular_term_exact(dshift<KIND>(D[l], sig), middle, __dmul_rn(w, w)));
+            }
+            S = block_allreduce(acc, OpSum(), red);
+        }
         if (KIND != KIND_DPR1) S = __dadd_rn(S, __ddiv_rn(1.0, __dadd_rn(0.0, -middle)));
         double F = __dadd_rn(1.0, __dmul_rn(R.rho, S));
         if (sr * F < 0.0) left = middle; else right = middle;
@@ -440,7 +448,17 @@ __device__ void solve_full(const Problem &P, const Outputs &O, int64_t k, int64_
                 double w = W[l];
                 acc = secular_term_acc(acc, dshift<KIND>(D[l], sigma), middle, __dmul_rn(w, w));
             }
-            double S = __dmul_rn(block_allreduce(acc, OpSum(), red), wz2);
+            double S = block_allreduce(acc, OpSum(), red);
+            if (S != S) {   // NaN from the reciprocal-seed term: redo the sweep with exact divisions (see secular_term_exact)
+                acc = 0.0;
+                for (int64_t l = tid; l < N; l += BT) {
+                    if (l == ii) continue;
+                    double w = W[l];
+                    acc = __dadd_rn(acc, secular_term_exact(dshift<KIND>(D[l], sigma), middle, __dmul_rn(w, w)));
+                }
+                S = block_allreduce(acc, OpSum(), red);
+            }
+            S = __dmul_rn(S, wz2);
             if (KIND != KIND_DPR1) S = __dadd_rn(S, __ddiv_rn(wz2, __dadd_rn(0.0, -middle)));
             double F = __dadd_rn(__dadd_rn(b, -middle), -S);
             if (F > 0.0) left = middle; else right = middle;

@@ -537,7 +537,20 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                 sum = __shfl_sync(0xffffffffu, sum, 0);
                 const double m = S.m;
                 bool goleft;
-                if (ROUND == 0) {
+                if (sum != sum) {
+                    // NaN: a term of this sweep was 0*Inf inside the reciprocal correction -- the bisection point sits
+                    // exactly on an inverse pole (possibly a pad pole's, for k = N+1) or d*(1-m*d) overflowed.  k_full
+                    // redoes the eigenpair from scratch and evaluates such sweeps with exact divisions.
+                    __syncwarp();
+                    if (lane == 0) {
+                        ks[S.k - kbase].flag = KS_HANDOFF;
+                        dlist[atomicAdd(dcount, 1ull)] = S.k;
+                        if (quantum > 0) atomicAdd(dcount + 5, 1ull);
+                        S.phase = PH_FREE;
+                    }
+                    __syncwarp();
+                    goleft = false;
+                } else if (ROUND == 0) {
                     sum = __dmul_rn(sum, S.wz2);
                     if (KIND != KIND_DPR1) sum = __dadd_rn(sum, __ddiv_rn(S.wz2, __dadd_rn(0.0, -m)));
                     goleft = __dadd_rn(__dadd_rn(S.b, -m), -sum) > 0.0;                  // arrowhead3.jl:696-701
@@ -547,7 +560,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                     goleft = sign_jl(S.b) * F < 0.0;
                 }
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && S.phase == PH_BISECT) {
                     if (goleft) S.left = m; else S.right = m;
                     S.m = (S.left + S.right) / 2.0;
                     S.steps += 1;
@@ -836,6 +849,7 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
             S.nu1 = nu1new; S.Kb = G.Kb; S.Kz = G.Kz; S.knu0 = G.knu; S.krho = R.Krho; S.sig2 = sigma1;
             __syncthreads();                           // every thread has read G before thread 0 rewrites it in the finalize
             int par = 0;
+            bool nanfail = false;
             while (!bisect_converged(S)) {
                 double acc = 0.0;
                 for (int tile = 0; tile < ntiles; ++tile) {
@@ -857,6 +871,7 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
                     sum = (lane & o) ? __dadd_rn(p, sum) : __dadd_rn(sum, p);
                 }
                 sum = __shfl_sync(0xffffffffu, sum, 0);
+                if (sum != sum) { nanfail = true; break; }   // as in k_bisect: k_full redoes this eigenpair
                 const double m = S.m;
                 if (KIND != KIND_DPR1) sum = __dadd_rn(sum, __ddiv_rn(1.0, __dadd_rn(0.0, -m)));
                 const double F = __dadd_rn(1.0, __dmul_rn(S.b, sum));
@@ -865,8 +880,12 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
                 S.steps += 1;
                 par ^= 1;
             }
-            if (tid == 0) { G.sigma = shift; G.krho = R.Krho; }   // k_vec reads sigma (the new shift), mu, lambda
-            bisect_finalize<KIND, 1>(P, O, ks, S, kbase, dlist, rlist, dcount, tid == 0 ? 0 : 1);
+            if (nanfail) {
+                if (tid == 0) { G.flag = KS_HANDOFF; dlist[atomicAdd(dcount, 1ull)] = k; }
+            } else {
+                if (tid == 0) { G.sigma = shift; G.krho = R.Krho; }   // k_vec reads sigma (the new shift), mu, lambda
+                bisect_finalize<KIND, 1>(P, O, ks, S, kbase, dlist, rlist, dcount, tid == 0 ? 0 : 1);
+            }
         }
         __syncthreads();
     }

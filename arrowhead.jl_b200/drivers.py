@@ -258,8 +258,20 @@ def eigen_symdpr1(A: SymDPR1, tau=None, *, ctx: Context | None = None, vectors="
 
 
 def svd_halfarrow(A: HalfArrow, tau=None, *, ctx: Context | None = None, vectors="host", forward_tau=False):
-    """svd(A::HalfArrow, tau) -> (SVD(U,S,Vt), Info).  The no-deflation path of arrowhead6.jl:526-661;
-    inputs with zeros in z or duplicate |D| (which the reference mishandles) raise."""
+    """svd(A::HalfArrow, tau) -> (SVD(U,S,Vt), Info)  (arrowhead6.jl:526-661).
+
+    Ordering by |D|, the sign row-scaling of V (:641) and the final permutation are the reference's.  Deflation:
+      * zeros in z (:569-584): sigma = |D_j|, u = e_j, v = sign(D_j) e_j -- the reference records these and then SKIPS
+        the solve of what remains (the `else` at :585 swallows it); here the remaining irreducible problem is solved;
+      * exact duplicates of |D| (:586-632): the reference's branch cannot run (its gap vector misses the last pair of
+        the no-tip shape, `zxxv=[zxx,n0+1]` nests a vector, the reduced HalfArrow loses the tip, the loop runs to
+        nn+1).  What it is after is done here the way eigen(::SymArrow) does it: one Givens rotation per duplicate
+        pair annihilates a border entry, the reduced problem is solved with row/column-mapped stores into the
+        identity-initialised U and V on the device, and the rotations are applied to the rows of U and V
+        (G' -- the algebraically consistent direction; V carries the signs of D already, so its rotation uses
+        s*sign(D_i1)*sign(D_i2)).
+    Not handled (the reference returns NaN there -- u = sigma*v./D divides by D, arrowhead6.jl:421): a zero in D next
+    to a nonzero z entry, or a zero tip entry; these raise ValueError."""
     ctx = ctx or get_context()
     D, z = A.D, A.z
     nd, n0 = D.size, z.size
@@ -269,20 +281,62 @@ def svd_halfarrow(A: HalfArrow, tau=None, *, ctx: Context | None = None, vectors
     Da = np.abs(D)
     is_ = jl_sortperm_desc(Da)
     Ds, sg = Da[is_].copy(), signD[is_].copy()
-    zs = z[is_].copy()
-    if np.any(zs == 0) or (tip and z[nd] == 0) or np.any(Ds[:-1] == Ds[1:]) or np.any(Ds == 0):
-        raise NotImplementedError("svd(HalfArrow): deflation (zeros in z/D or duplicate |D|) is outside the "
-                                  "hot path; the reference's own deflation branch does not run (arrowhead6.jl:569-632)")
-    zfull = np.concatenate([zs, [z[nd]]]) if tip else zs
+    zs = z[:nd][is_].copy()
     want = vectors is not None
     nu_rows, nv_rows = n0, (n0 if tip else n0 + 1)
-    Udev = DeviceMatrix(ctx, nu_rows, n0) if want else None
-    Vdev = DeviceMatrix(ctx, nv_rows, n0) if want else None
-    res = ctx.halfarrow(Ds, zfull, tau_k, vectors=False, U_dev=Udev.ptr if want else None, ldu=nu_rows,
-                        V_dev=Vdev.ptr if want else None, ldv=nv_rows, rowscale_v=sg if want else None)
-    S = res.lam.copy()
+    if (tip and z[nd] == 0) or np.any((Ds == 0) & (zs != 0)):
+        raise ValueError("svd(HalfArrow): a zero tip entry or a zero in D beside a nonzero z entry makes the reference "
+                         "divide by zero (arrowhead6.jl:421-424); deflate it before calling")
+    S = np.zeros(n0)
     info = Info.zeros(n0)
-    info.scatter(np.arange(n0), res)
+    z0 = np.flatnonzero(zs == 0)
+    zx = np.flatnonzero(zs != 0)
+    res = None
+    if z0.size == 0 and not np.any(Ds[:-1] == Ds[1:]):
+        # ---- no deflation: the loop of arrowhead6.jl:635-642 in one call
+        zfull = np.concatenate([zs, [z[nd]]]) if tip else zs
+        Udev = DeviceMatrix(ctx, nu_rows, n0) if want else None
+        Vdev = DeviceMatrix(ctx, nv_rows, n0) if want else None
+        res = ctx.halfarrow(Ds, zfull, tau_k, vectors=False, U_dev=Udev.ptr if want else None, ldu=nu_rows,
+                            V_dev=Vdev.ptr if want else None, ldv=nv_rows, rowscale_v=sg if want else None)
+        S[:] = res.lam
+        info.scatter(np.arange(n0), res)
+    else:
+        Udev = DeviceMatrix(ctx, nu_rows, n0) if want else None
+        Vdev = DeviceMatrix(ctx, nv_rows, n0) if want else None
+        if want:
+            ctx.set_identity(Udev.ptr, nu_rows, n0, nu_rows)
+            ctx.set_identity(Vdev.ptr, nv_rows, n0, nv_rows)
+        neg = []                                          # deflated columns whose v = -e_j
+        S[z0] = Ds[z0]
+        neg += [int(j) for j in z0 if sg[j] < 0]
+        Dr, zr = Ds[zx].copy(), zs[zx].copy()
+        if zx.size == 0:
+            if tip:                                       # only the tip row is left (arrowhead6.jl:577-580)
+                S[n0 - 1] = abs(z[nd])
+                if z[nd] < 0:
+                    neg.append(n0 - 1)
+            rots = []
+        else:
+            keep, rots = _deflate_duplicates(Dr, zr, zx, S, "transpose")
+            dup = np.setdiff1d(np.arange(zx.size), keep)
+            neg += [int(zx[p]) for p in dup if sg[zx[p]] < 0]
+            rows = zx[keep]
+            zk = np.concatenate([zr[keep], [z[nd]]]) if tip else zr[keep]
+            rowmap_u = np.concatenate([rows, [n0 - 1]]) if tip else rows
+            rowmap_v = np.concatenate([rows, [nv_rows - 1]])
+            res = ctx.halfarrow(Dr[keep], zk, tau_k, vectors=False, U_dev=Udev.ptr if want else None, ldu=nu_rows,
+                                V_dev=Vdev.ptr if want else None, ldv=nv_rows, rowmap_u=rowmap_u if want else None,
+                                rowmap_v=rowmap_v if want else None, rowscale_v=sg[rows] if want else None)
+            S[rowmap_u] = res.lam
+            info.scatter(rowmap_u, res)
+        if want:
+            minus = np.array([-1.0])
+            for j in neg:                                 # V[j,j] = sign(D_j) (arrowhead6.jl:572-574)
+                ctx.memcpy_h2d(Vdev.ptr + 8 * (j * nv_rows + j), minus, 8)
+            for (i1, i2, c, s) in rots:
+                ctx.apply_givens_rows(Udev.ptr, Udev.ld, n0, i1, i2, c, s)
+                ctx.apply_givens_rows(Vdev.ptr, Vdev.ld, n0, i1, i2, c, s * sg[i1] * sg[i2])
     isi = np.argsort(is_, kind="stable").astype(np.int64)
     es = jl_sortperm_desc(S)
     rows_u = isi if not tip else np.concatenate([isi, [n0 - 1]])
@@ -291,7 +345,7 @@ def svd_halfarrow(A: HalfArrow, tau=None, *, ctx: Context | None = None, vectors
     Vo = _finish(ctx, Vdev, rows_v, es, vectors)
     Vt = None if Vo is None else (Vo.T if isinstance(Vo, np.ndarray) else Vo)   # device: V itself (Vt is its transpose)
     out_info = info.permuted(es)
-    out_info.stats = res.stats
+    out_info.stats = res.stats if res is not None else None
     return SVD(Uo, S[es], Vt), out_info
 
 

@@ -258,7 +258,7 @@ def eigen_symdpr1(D, u, r, lib=None, nthreads=0, rotation="reference") -> EigenR
 
 
 # ------------------------------------------------------------------------------------------ HalfArrow
-def svd_halfarrow(D, z, lib=None, nthreads=0, rotation="reference") -> SVDResult:
+def svd_halfarrow(D, z, lib=None, nthreads=0, rotation="transpose") -> SVDResult:
     """svd(A::HalfArrow,tau), arrowhead6.jl:526-661 (no-deflation path exact; deflation by intent)."""
     lib = lib or get_lib()
     D = np.asarray(D, np.float64)
@@ -296,14 +296,16 @@ def svd_halfarrow(D, z, lib=None, nthreads=0, rotation="reference") -> SVDResult
         else:
             zxv = np.concatenate([zx, [n0]])
         ndr = Ds.size
+        # Exact-duplicate deflation, BY INTENT.  The reference's branch (arrowhead6.jl:586-632) cannot run: its gap
+        # vector `D[1:n-2]-D[2:n-1]` misses the last pair of the no-tip shape, `zxxv=[zxx,n0+1]` nests a vector in a
+        # vector, the reduced HalfArrow drops the tip and the loop runs to nn+1.  What it is after -- rotate the two
+        # rows of a duplicate |D| so that one border entry vanishes, solve the reduced problem, rotate U AND V back --
+        # is done here for every duplicate pair.
         g = Ds[:-1] - Ds[1:]
-        if not tip:
-            g = g[: max(ndr - 2, 0)]                # arrowhead6.jl:594 omits the last pair w/o tip
         g0 = np.flatnonzero(g == 0)
-        if g0.size:                                 # arrowhead6.jl:601-632 (`zxxv=[zxx,n0+1]` nests)
+        if g0.size:
             ref_throws = True
-            gx = np.flatnonzero((Ds[:-1] - Ds[1:]) != 0) if tip else np.concatenate(
-                [np.flatnonzero(g != 0), np.arange(max(ndr - 2, 0), ndr - 1)])
+            gx = np.flatnonzero(g != 0)
             rots = [None] * g0.size
             for l in range(g0.size - 1, -1, -1):
                 p = g0[l]
@@ -324,9 +326,11 @@ def svd_halfarrow(D, z, lib=None, nthreads=0, rotation="reference") -> SVDResult
                 V[rows_v, col] = res.V[:, c]
                 V[rows_v[:-1], col] *= sgn[keep]
                 info.set_from(col, res, c)
-            for (i1, i2, c, s) in rots:             # intent: rotate both factors
+            # A = B*diag(signD,1) with B = HalfArrow(|D|,z): B = G'*Bnew*G~ for a duplicate |D| pair, so U = G'*Unew and
+            # W = G~'*Wnew; the stored V = diag(signD,1)*W carries the signs already, hence s -> s*signD[i1]*signD[i2]
+            for (i1, i2, c, s) in rots:
                 _apply_givens_rows(U, i1, i2, c, s, rotation)
-                _apply_givens_rows(V, i1, i2, c, s, rotation)
+                _apply_givens_rows(V, i1, i2, c, s * signD[i1] * signD[i2], rotation)
         else:
             res = lib.halfarrow(Ds, zs, default_tau(ndr), nthreads=nthreads)
             for c in range(zx.size):

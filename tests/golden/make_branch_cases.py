@@ -9,7 +9,13 @@ taken in bits 8..14 of its status word) which branch an input takes.  The inputs
 tests/golden/branch_cases.json together with the oracle's status words; tests/test_branches.py re-runs the oracle on
 them (CPU) and requires the CUDA path to take the same branch for every eigenpair (GPU).
 
-    python tests/golden/make_branch_cases.py
+Two of the branches -- "Remedy 3 once more" and the 'R'->'L' retry -- are decided by quantities that are pure rounding
+noise after a first stage with K_nu ~ 1/eps (the re-shift lands on either side of the eigenvalue), so the oracle and the
+CUDA path need not take them on the same input.  When a GPU is present (`--gpu`, run on the B200 box) a candidate for
+those two targets is accepted only if the library takes the branch as well; the fixture then pins an input on which
+both do.
+
+    python tests/golden/make_branch_cases.py [--gpu]
 """
 import json
 import os
@@ -85,18 +91,36 @@ def candidates(rng):
             yield "halfarrow", Dh, w, None
 
 
+NOISY = ("REM3_REPEAT", "RL_RETRY")
+
+
+def gpu_status(ctx, kind, D, w, top):
+    if kind == "symarrow":
+        return ctx.symarrow(D, w, top, vectors=False).status
+    if kind == "symdpr1":
+        return ctx.symdpr1(D, w, top, vectors=False).status
+    return ctx.halfarrow(D, w, vectors=False).status
+
+
 def main():
     lib = oracle.get_lib()
+    ctx = None
+    if "--gpu" in sys.argv:
+        import arrowhead_b200 as ab
+        ctx = ab.get_context(0)
     rng = np.random.default_rng(20261020)
     need = {(kind, t) for kind, ts in TARGETS.items() for t in ts}
     cases = []
     tried = 0
     for kind, D, w, top in candidates(rng):
         tried += 1
-        if tried > 400000 or not need:
+        if tried > 1500000 or not need:
             break
         O = run(lib, kind, D, w, top)
         hit = [t for t in TARGETS[kind] if (kind, t) in need and ((O.status & BITS[t]) != 0).any()]
+        if ctx is not None and any(t in NOISY for t in hit):
+            gs = gpu_status(ctx, kind, D, w, top)
+            hit = [t for t in hit if t not in NOISY or np.array_equal(gs & ~32, O.status)]      # same branch trace for every k
         if not hit:
             continue
         for t in hit:
@@ -107,7 +131,7 @@ def main():
     if need:
         print("NOT FOUND:", sorted(need))
     with open(os.path.join(HERE, "branch_cases.json"), "w", encoding="utf-8") as f:
-        json.dump({"bits": BITS, "not_found": sorted(list(x) for x in need), "cases": cases}, f, indent=1)
+        json.dump({"bits": BITS, "not_found": sorted(list(x) for x in need), "gpu_checked": ctx is not None, "cases": cases}, f, indent=1)
 
 
 if __name__ == "__main__":

@@ -199,3 +199,32 @@ def compare_range(gpu, orc, hi=None, *, lam_tol=10.0, vec_tol=100.0, k_tol=1e-9,
         assert np.all(col_err[ok] <= (bar[ok] if np.ndim(bar) else bar)), \
             f"{vname} entry error {col_err[worst]:.1f} eps > bar {np.atleast_1d(bar)[worst]:.1f} at k={gpu.k0 + worst} (Knu={knu[worst]:.1f})"
     return out
+
+
+def halfarrow_deflation_cases():
+    """(name, D, z) inputs for svd(::HalfArrow) with zeros in z and exact duplicates of |D| (equal and opposite signs,
+    a triple, in the last pair), both shapes.  Used by the oracle-driver (CPU) and product-driver (GPU) tests."""
+    rng = np.random.default_rng(77)
+    out = []
+    for tip in (0, 1):
+        t = [0.7] if tip else []
+        out.append((f"z zero tip={tip}", np.array([3.0, -2.0, 1.5, 0.5]), np.array([1.0, 0.0, -0.5, 0.0] + t)))
+        out.append((f"dup same sign tip={tip}", np.array([3.0, 2.0, 2.0, 0.5]), np.array([1.0, 2.0, -0.5, 0.25] + t)))
+        out.append((f"dup opposite sign tip={tip}", np.array([3.0, -2.0, 2.0, 0.5]), np.array([1.0, 2.0, -0.5, 0.25] + t)))
+        out.append((f"triple tip={tip}", np.array([1.0, 2.0, -2.0, 2.0, 0.5, 4.0]), np.array([1.0, 2.0, -0.5, 0.25, 0.3, -1.0] + t)))
+        out.append((f"dup last pair tip={tip}", np.array([3.0, 2.0, 0.5, 0.5]), np.array([1.0, 2.0, -0.5, 0.25] + t)))
+        out.append((f"dup + z zero tip={tip}", np.array([3.0, 2.0, -2.0, 0.5, 0.5, 7.0]), np.array([1.0, 0.0, -0.5, 0.25, 1.0, 0.0] + t)))
+        out.append((f"all z zero tip={tip}", np.array([3.0, -2.0, 0.5]), np.array([0.0, 0.0, 0.0] + t)))
+        D = (np.round(rng.random(40) * 8) / 4 + 0.25) * np.where(rng.random(40) < 0.5, -1, 1)   # many exact duplicates of |D|
+        z = np.where(rng.random(40) < 0.2, 0.0, rng.random(40) - 0.5)
+        out.append((f"random grid tip={tip}", D, np.concatenate([z, t])))
+    return out
+
+
+def halfarrow_dense(D, z):
+    """[Diagonal(D) z[1:nd]] (no tip: nd x nd+1) or the same with the row [0 ... 0 z[nd+1]] appended (tip)."""
+    nd = D.size
+    A = np.zeros((z.size, nd + 1))
+    A[np.arange(nd), np.arange(nd)] = D
+    A[:, nd] = z
+    return A
