@@ -10,7 +10,7 @@ include/arrowhead_b200.h); there is no CPU fallback.
 from .types import (SVD, Eigen, GenHalfArrow, GenHermArrow, GenHermDPR1, GenSymArrow, GenSymDPR1, HalfArrow,  # noqa: F401
                     HermArrow, HermDPR1, Info, SymArrow,
                     SymDPR1)
-from ._lib import (LIB_PATH, ArrowheadError, Context, get_context, load_library, EXPORTS,  # noqa: F401
+from ._lib import (LIB_PATH, ArrowheadError, Context, MultiContext, get_context, load_library, EXPORTS,  # noqa: F401
                    ST_NU_INF, ST_NEEDS_BIGFLOAT, ST_POLE_RETURN, ST_REF_THROWS, ST_ITER_LIMIT, ST_INTERLACE)
 from .drivers import (DeviceMatrix, eigen, eigen_hermarrow, eigen_hermdpr1, eigen_symarrow, eigen_symdpr1, givens, jl_sortperm_desc,  # noqa: F401
                       svd, svd_halfarrow, tdc, tdc_device, tdc_recursive)

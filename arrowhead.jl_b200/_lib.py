@@ -52,6 +52,9 @@ EXPORTS = [
     "ah_scale_rows_phase", "ah_symarrow_eigvals_dd", "ah_symarrow_eigen_batched", "ah_gather_elements", "ah_gather_permuted_batched",
     "ah_copy2d_batched", "ah_dgemm_batched",
     "ah_measure_fp64_peak", "ah_measure_term_peak", "ah_measure_store_bw",
+    "ah_multi_create", "ah_multi_destroy", "ah_multi_ndev", "ah_multi_ctx", "ah_multi_last_error", "ah_multi_elapsed_ms",
+    "ah_k_partition", "ah_multi_symarrow_eigen", "ah_multi_symdpr1_eigen", "ah_multi_halfarrow_svd",
+    "ah_multi_allgather_columns", "ah_nccl_unique_id", "ah_nccl_init", "ah_allgather_columns",
 ]
 
 
@@ -104,10 +107,31 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ah_measure_fp64_peak.argtypes = [vp, _dp, _dp]
     lib.ah_measure_term_peak.argtypes = [vp, _dp, _dp]
     lib.ah_measure_store_bw.argtypes = [vp, C.c_int64, _dp]
+    pp = C.POINTER(vp)
+    lib.ah_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    lib.ah_multi_destroy.argtypes = [vp]
+    lib.ah_multi_ndev.argtypes = [vp]
+    lib.ah_multi_ctx.argtypes = [vp, C.c_int]
+    lib.ah_multi_last_error.argtypes = [vp]
+    lib.ah_multi_elapsed_ms.argtypes = [vp]
+    lib.ah_k_partition.argtypes = [C.c_int64, C.c_int, C.c_int, _i64p, _i64p]
+    lib.ah_multi_symarrow_eigen.argtypes = [vp, C.c_int64, _dp, _dp, C.c_double, _dp, C.POINTER(AhResult), pp]
+    lib.ah_multi_symdpr1_eigen.argtypes = [vp, C.c_int64, _dp, _dp, C.c_double, _dp, C.POINTER(AhResult), pp]
+    lib.ah_multi_halfarrow_svd.argtypes = [vp, C.c_int64, C.c_int64, _dp, _dp, _dp, C.POINTER(AhResult), pp, pp]
+    lib.ah_multi_allgather_columns.argtypes = [vp, pp, C.c_int64, C.c_int64, _dp]
+    lib.ah_nccl_unique_id.argtypes = [vp]
+    lib.ah_nccl_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.ah_allgather_columns.argtypes = [vp, vp, C.c_int64, C.c_int64, _dp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("ah_destroy", "ah_last_error"):
+        if name not in ("ah_destroy", "ah_last_error", "ah_multi_destroy", "ah_multi_ctx", "ah_multi_last_error", "ah_multi_elapsed_ms",
+                        "ah_k_partition"):
             fn.restype = C.c_int
+    lib.ah_multi_destroy.restype = None
+    lib.ah_k_partition.restype = None
+    lib.ah_multi_ctx.restype = vp
+    lib.ah_multi_last_error.restype = C.c_char_p
+    lib.ah_multi_elapsed_ms.restype = C.c_double
     return lib
 
 
@@ -338,6 +362,23 @@ class Context:
     def pinned_free(self, ptr):
         self._check(self.lib.ah_host_free_pinned(self.handle, C.c_void_p(ptr)))
 
+    # ---- NCCL all-gather of U, one process per GPU (ah_nccl_init once, then ah_allgather_columns) ----------
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.ah_nccl_unique_id(buf)
+        if rc != 0:
+            raise ArrowheadError(rc, (self.lib.ah_last_error(None) or b"").decode())
+        return buf.raw
+
+    def nccl_init(self, nranks: int, rank: int, uid: bytes):
+        buf = C.create_string_buffer(bytes(uid), 128)
+        self._check(self.lib.ah_nccl_init(self.handle, int(nranks), int(rank), buf))
+
+    def allgather_columns(self, U_full_dev, ld, kmax) -> float:
+        ms = C.c_double()
+        self._check(self.lib.ah_allgather_columns(self.handle, C.c_void_p(int(U_full_dev)), int(ld), int(kmax), C.byref(ms)))
+        return ms.value
+
     def measure_fp64_peak(self):
         g, ms = C.c_double(), C.c_double()
         self._check(self.lib.ah_measure_fp64_peak(self.handle, C.byref(g), C.byref(ms)))
@@ -352,6 +393,114 @@ class Context:
         g = C.c_double()
         self._check(self.lib.ah_measure_store_bw(self.handle, nbytes, C.byref(g)))
         return g.value
+
+
+class MultiContext:
+    """ah_multi: several GPUs driven from this one thread (worker threads live inside the library)."""
+
+    def __init__(self, devices=None, ndev: int = 0, lib: C.CDLL | None = None):
+        self.lib = lib or load_library()
+        self.handle = C.c_void_p()
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.ah_multi_create(C.byref(self.handle), arr, len(devices))
+        else:
+            rc = self.lib.ah_multi_create(C.byref(self.handle), None, int(ndev))
+        if rc != 0:
+            raise ArrowheadError(rc, (self.lib.ah_last_error(None) or b"").decode())
+        self.ndev = int(self.lib.ah_multi_ndev(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.ah_multi_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ArrowheadError(rc, (self.lib.ah_multi_last_error(self.handle) or b"").decode())
+
+    def partition(self, kmax: int, r: int):
+        k0, k1 = C.c_int64(), C.c_int64()
+        self.lib.ah_k_partition(int(kmax), self.ndev, int(r), C.byref(k0), C.byref(k1))
+        return k0.value, k1.value
+
+    def device_stats(self, r: int) -> dict:
+        s = AhStats()
+        rc = self.lib.ah_get_stats(C.c_void_p(self.lib.ah_multi_ctx(self.handle, int(r))), C.byref(s))
+        if rc != 0:
+            raise ArrowheadError(rc, "ah_get_stats")
+        return s.asdict()
+
+    def _ptrs(self, bufs):
+        if bufs is None:
+            return None, None
+        arr = (C.c_void_p * self.ndev)(*[C.c_void_p(int(b)) for b in bufs])
+        return arr, C.cast(arr, C.POINTER(C.c_void_p))
+
+    def _solve(self, fn, args, kmax, nrows_u, nrows_v, vectors, U_full, V_full, U_host, ldu, V_host=None, ldv=0):
+        res = RangeResult(1, kmax)
+        r = AhResult()
+        res.fill(r)
+        if U_full is None:
+            if U_host is not None:
+                r.U, r.ldu, r.U_mem = C.c_void_p(int(U_host)), int(ldu), AH_MEM_HOST
+            elif vectors:
+                res.U = np.zeros((nrows_u, kmax), order="F")
+                r.U, r.ldu, r.U_mem = res.U.ctypes.data_as(C.c_void_p), nrows_u, AH_MEM_HOST
+        else:
+            r.ldu = int(ldu or nrows_u)
+        if nrows_v:
+            if V_full is None:
+                if V_host is not None:
+                    r.V, r.ldv, r.V_mem = C.c_void_p(int(V_host)), int(ldv), AH_MEM_HOST
+                elif vectors:
+                    res.V = np.zeros((nrows_v, kmax), order="F")
+                    r.V, r.ldv, r.V_mem = res.V.ctypes.data_as(C.c_void_p), nrows_v, AH_MEM_HOST
+            else:
+                r.ldv = int(ldv or nrows_v)
+        ku, pu = self._ptrs(U_full)
+        extra = (pu,)
+        if nrows_v:
+            kv, pv = self._ptrs(V_full)
+            extra = (pu, pv)
+        self._check(fn(self.handle, *args, C.byref(r), *extra))
+        res.stats = {"elapsed_ms": float(self.lib.ah_multi_elapsed_ms(self.handle)),
+                     "devices": [self.device_stats(i) for i in range(self.ndev)]}
+        return res
+
+    def symarrow(self, D, z, a, tau=None, vectors=True, U_full=None, U_host=None, ldu=0):
+        D = np.ascontiguousarray(D, np.float64); z = np.ascontiguousarray(z, np.float64)
+        tau_a = None if tau is None else np.ascontiguousarray(tau, np.float64)
+        N = D.size
+        args = (C.c_int64(N), _ptr(D, _dp), _ptr(z, _dp), C.c_double(float(a)), _ptr(tau_a, _dp))
+        return self._solve(self.lib.ah_multi_symarrow_eigen, args, N + 1, N + 1, 0, vectors, U_full, None, U_host, ldu)
+
+    def symdpr1(self, D, u, rho, tau=None, vectors=True, U_full=None, U_host=None, ldu=0):
+        D = np.ascontiguousarray(D, np.float64); u = np.ascontiguousarray(u, np.float64)
+        tau_a = None if tau is None else np.ascontiguousarray(tau, np.float64)
+        n = D.size
+        args = (C.c_int64(n), _ptr(D, _dp), _ptr(u, _dp), C.c_double(float(rho)), _ptr(tau_a, _dp))
+        return self._solve(self.lib.ah_multi_symdpr1_eigen, args, n, n, 0, vectors, U_full, None, U_host, ldu)
+
+    def halfarrow(self, D, z, tau=None, vectors=True, U_full=None, V_full=None, ldu=0, ldv=0):
+        D = np.ascontiguousarray(D, np.float64); z = np.ascontiguousarray(z, np.float64)
+        tau_a = None if tau is None else np.ascontiguousarray(tau, np.float64)
+        nd, nz = D.size, z.size
+        args = (C.c_int64(nd), C.c_int64(nz), _ptr(D, _dp), _ptr(z, _dp), _ptr(tau_a, _dp))
+        return self._solve(self.lib.ah_multi_halfarrow_svd, args, nz, nz, nd + 1, vectors, U_full, V_full, None, ldu, None, ldv)
+
+    def allgather_columns(self, U_full, ld, kmax) -> float:
+        """in-place NCCL all-gather of the column blocks of the per-device full-size buffers; returns device ms"""
+        keep, pu = self._ptrs(U_full)
+        ms = C.c_double()
+        self._check(self.lib.ah_multi_allgather_columns(self.handle, pu, int(ld), int(kmax), C.byref(ms)))
+        return ms.value
 
 
 _CTX: dict[int, Context] = {}

@@ -66,6 +66,8 @@ struct ah_ctx {
     std::vector<cudaEvent_t> chunk_ev;   // 5 timing events per column block of the current call
     unsigned long long *hCounts = nullptr;  // pinned, 2 per column block: hand-over / Remedy-3 counts of the last call
     size_t hCountsCap = 0;
+    void *nccl_comm = nullptr;              // ncclComm_t of ah_nccl_init (one process per GPU); see ah_multi.inl
+    int nccl_rank = 0, nccl_nranks = 0;
 };
 
 namespace {
@@ -131,6 +133,10 @@ hdd h_add(hdd x, hdd y) {  // DoubleDouble.jl:112-116
                                                          : (((y.hi - r) + x.hi) + x.lo) + y.lo;
     return h_renorm(r, s);
 }
+
+}  // namespace
+void ah_release_nccl(ah_ctx *ctx);   // ah_multi.inl
+namespace {
 
 struct Timer {
     cudaEvent_t a, b;
@@ -719,6 +725,7 @@ void ah_destroy(ah_ctx *ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (auto &ev : ctx->side_ev) cudaEventDestroy(ev);
+    ah_release_nccl(ctx);
     delete ctx;
 }
 
@@ -1194,3 +1201,5 @@ int ah_measure_store_bw(ah_ctx *ctx, int64_t bytes, double *gb_per_s) {
 }
 
 }  // extern "C"
+
+#include "ah_multi.inl"

@@ -122,8 +122,8 @@ function solve!(Λ::Vector{Float64}, U::Matrix{Float64}, κ::Vector{Info}, Ax::S
                         ctx(), N, Ax.D, Ax.z, Ax.a, C_NULL, 1, n, r))
         else
             check(ccall((:ah_multi_symarrow_eigen, LIB), Cint,
-                        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ref{AhResult}),
-                        m, N, Ax.D, Ax.z, Ax.a, C_NULL, r))
+                        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ref{AhResult}, Ptr{Ptr{Float64}}),
+                        m, N, Ax.D, Ax.z, Ax.a, C_NULL, r, C_NULL))
         end
     end
     redo = report(o, "eigen(::SymArrow)")
@@ -167,8 +167,8 @@ function solve!(Λ::Vector{Float64}, U::Matrix{Float64}, κ::Vector{Info}, Ax::S
                         ctx(), n, Ax.D, Ax.u, Ax.r, C_NULL, 1, n, r))
         else
             check(ccall((:ah_multi_symdpr1_eigen, LIB), Cint,
-                        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ref{AhResult}),
-                        m, n, Ax.D, Ax.u, Ax.r, C_NULL, r))
+                        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ref{AhResult}, Ptr{Ptr{Float64}}),
+                        m, n, Ax.D, Ax.u, Ax.r, C_NULL, r, C_NULL))
         end
     end
     redo = report(o, "eigen(::SymDPR1)")
@@ -218,8 +218,8 @@ function solve!(Σ::Vector{Float64}, U::Matrix{Float64}, V::Matrix{Float64}, κ:
                         ctx(), nd, nz, Ax.D, Ax.z, C_NULL, 1, nz, r))
         else
             check(ccall((:ah_multi_halfarrow_svd, LIB), Cint,
-                        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{AhResult}),
-                        m, nd, nz, Ax.D, Ax.z, C_NULL, r))
+                        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{AhResult}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}),
+                        m, nd, nz, Ax.D, Ax.z, C_NULL, r, C_NULL, C_NULL))
         end
     end
     redo = report(o, "svd(::HalfArrow)")

@@ -153,6 +153,44 @@ int ah_halfarrow_svd(ah_ctx *ctx, int64_t nd, int64_t nz, const double *D, const
  * the context (batched solves, ah_symarrow_eigvals_dd) invalidates the resident inputs. */
 int ah_resolve(ah_ctx *ctx, int64_t k0, int64_t k1, ah_result *out);
 
+/* ---- several GPUs ------------------------------------------------------------------------------
+ * The reference parallelises the eigenpair loop inside one process (`Threads.@threads for k`, arrowhead3.jl:641-644,
+ * arrowhead4.jl:531-535).  ah_multi does the same over GPUs for a single-threaded caller (Julia's ccall): one context
+ * per device, one worker thread per context inside the library, the k-range 1..kmax cut into contiguous blocks
+ * (ah_k_partition).  Every device receives D and z and owns its eigenpairs and its columns of U; nothing is exchanged.
+ *   out->lambda / sind / ... : host arrays of FULL length kmax; device r fills its block.
+ *   eigenvectors, host   : out->U (out->U_mem = AH_MEM_HOST) is the full host matrix; every device streams its columns
+ *                          into it (ld = out->ldu).  Pass U_full = NULL.
+ *   eigenvectors, device : U_full[r] is a full-size buffer (ldu x kmax doubles) on device r; device r writes its block
+ *                          at column offset k0-1, so that ah_multi_allgather_columns can complete every copy in place.
+ * Mapped stores (rowmap_u/rowmap_v: deflated problems) are not sharded.  Calls block until every device has finished;
+ * ah_multi_last_error gives the first failure; per-device timing: ah_get_stats(ah_multi_ctx(m, r), ...). */
+typedef struct ah_multi ah_multi;
+int  ah_multi_create(ah_multi **m, const int *devices, int ndev);   /* devices NULL: 0..ndev-1; ndev <= 0: all visible GPUs */
+void ah_multi_destroy(ah_multi *m);
+int  ah_multi_ndev(const ah_multi *m);
+ah_ctx *ah_multi_ctx(ah_multi *m, int r);                           /* borrowed; r = 0..ndev-1 */
+const char *ah_multi_last_error(const ah_multi *m);
+double ah_multi_elapsed_ms(const ah_multi *m);                      /* host wall time of the last ah_multi_* solve */
+/* block r of nparts: the 1-based inclusive range [*k0,*k1] (sizes differ by at most one; empty: k0=1, k1=0) */
+void ah_k_partition(int64_t nk, int nparts, int r, int64_t *k0, int64_t *k1);
+int ah_multi_symarrow_eigen(ah_multi *m, int64_t N, const double *D, const double *z, double a, const double *tau,
+                            ah_result *out, double *const *U_full);
+int ah_multi_symdpr1_eigen(ah_multi *m, int64_t n, const double *D, const double *u, double rho, const double *tau,
+                           ah_result *out, double *const *U_full);
+int ah_multi_halfarrow_svd(ah_multi *m, int64_t nd, int64_t nz, const double *D, const double *z, const double *tau,
+                           ah_result *out, double *const *U_full, double *const *V_full);
+/* In-place all-gather over NVLink (ncclAllGather; ncclBroadcast per block when kmax is not a multiple of ndev): after
+ * the call every U_full[r] (ld x kmax, column-major, on device r) holds all columns.  *elapsed_ms: device time, max
+ * over the devices.  NCCL is dlopen()ed on first use (libnccl.so.2; env ARROWHEAD_B200_NCCL overrides the path). */
+int ah_multi_allgather_columns(ah_multi *m, double *const *U_full, int64_t ld, int64_t kmax, double *elapsed_ms);
+/* The same for one process per GPU (torchrun / MPI style): rank 0 calls ah_nccl_unique_id, the caller carries the
+ * 128 bytes to the other ranks, everyone calls ah_nccl_init once, then ah_allgather_columns on its own full-size
+ * buffer whose block [ah_k_partition(kmax, nranks, rank)] it has filled. */
+int ah_nccl_unique_id(void *id128);
+int ah_nccl_init(ah_ctx *ctx, int nranks, int rank, const void *id128);
+int ah_allgather_columns(ah_ctx *ctx, double *U_full, int64_t ld, int64_t kmax, double *elapsed_ms);
+
 /* ---- device utilities for a resident U -------------------------------------------------------- */
 int ah_device_malloc(ah_ctx *ctx, void **dptr, int64_t bytes);
 int ah_device_free(ah_ctx *ctx, void *dptr);
