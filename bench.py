@@ -8,8 +8,11 @@ One step = one full eigendecomposition of the synthetic ordered SymArrow (SURVEY
 descending, arrow top last).  With N GPUs the eigenpair range 1..n is split into N contiguous blocks
 (`k_partition`), every rank gets D,z,a and owns its block of U's columns; no collective is on the data path,
 total work is fixed ("strong" scaling).  `value` is device-timed (CUDA events on the launching stream, max
-over ranks) with inputs passed as host arrays of 0.5 MB and U left resident in HBM; `e2e` goes through the
-same C-ABI call with the eigenvectors copied back into pinned host memory every step.
+over ranks) around the drop-in boundary call itself (ah_symarrow_eigen: host D, z of 0.5 MB validated, padded and
+uploaded every step) with U left resident in HBM -- the figure with D, z already resident (ah_resolve) is reported
+beside it in `config.value_resident_inputs`; `e2e` goes through the same C-ABI call with the eigenvectors copied
+back into pinned host memory every step.  `--workload symdpr1|halfarrow` run BASELINE configs[2] / [3] (default
+n = 16384) through the same harness; the default run appends the n = 65536 target as `target_n65536`.
 """
 from __future__ import annotations
 
@@ -157,6 +160,187 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def gen_symdpr1(n, seed=421):
+    rng = np.random.default_rng(seed)
+    D = np.sort(rng.random(n))[::-1].copy()
+    u = rng.random(n)
+    rho = float(rng.random())
+    return D, u, rho
+
+
+def gen_halfarrow(nd, seed=421):
+    rng = np.random.default_rng(seed)
+    D = np.sort(np.abs(rng.random(nd) - 0.5))[::-1].copy()
+    z = rng.random(nd + 1) - 0.5
+    return D, z
+
+
+class Problem:
+    """one of the three matrix types of the hot path at order n (number of eigenpairs / singular triples = n)"""
+
+    def __init__(self, kind, n):
+        self.kind, self.n = kind, n
+        if kind == "symarrow":
+            self.D, self.z, self.a = gen_symarrow(n)
+            self.npoles, self.ncols_v = n - 1, 0
+            self.metric = METRIC % n
+            self.workload = f"SymArrow n={n} full eigen(), GenSymArrow-like rng(421), ordered, arrow top last"
+            self.entry = "ah_symarrow_eigen"
+        elif kind == "symdpr1":
+            self.D, self.z, self.a = gen_symdpr1(n)
+            self.npoles, self.ncols_v = n, 0
+            self.metric = f"SymDPR1 n={n} full eigen(): eigenpairs/s"
+            self.workload = f"SymDPR1 n={n} full eigen(), GenSymDPR1-like rng(421), ordered, rho > 0"
+            self.entry = "ah_symdpr1_eigen"
+        else:
+            self.D, self.z = gen_halfarrow(n - 1)
+            self.a = None
+            self.npoles, self.ncols_v = n - 1, n
+            self.metric = f"HalfArrow length(z)={n} full svd(): singular triples/s"
+            self.workload = f"HalfArrow nd={n - 1}, length(z)=nd+1={n} (SVD-update shape) full svd(), rng(421), ordered"
+            self.entry = "ah_halfarrow_svd"
+
+    def solve(self, ctx, k0, k1, U, V=None, host=False, D=None, z=None):
+        D = self.D if D is None else D
+        z = self.z if z is None else z
+        kw = {("U_host" if host else "U_dev"): U, "ldu": self.n}
+        if self.kind == "symarrow":
+            return ctx.symarrow(D, z, self.a, k0=k0, k1=k1, vectors=False, **kw)
+        if self.kind == "symdpr1":
+            return ctx.symdpr1(D, z, self.a, k0=k0, k1=k1, vectors=False, **kw)
+        return ctx.halfarrow(D, z, k0=k0, k1=k1, vectors=False, U_dev=U, ldu=self.n, V_dev=V, ldv=self.n)
+
+    def resolve(self, ctx, k0, k1, U, V=None):
+        if self.kind == "halfarrow":
+            return ctx.resolve(k0, k1, vectors=False, U_dev=U, ldu=self.n, V_dev=V, ldv=self.n)
+        return ctx.resolve(k0, k1, vectors=False, U_dev=U, ldu=self.n)
+
+    @property
+    def vec_bytes(self):
+        return self.n * 8 * (2 if self.kind == "halfarrow" else 1)
+
+
+def fp64_denominator(ctx, sampler_index):
+    """The FP64 roofline denominator, measured live and put on record: a dependent-free DFMA burst on every SM
+    (ah_measure_fp64_peak, 8 independent chains x 512 threads x 4 CTAs per SM) with the SM clock sampled while it runs."""
+    smp = ClockSampler(sampler_index)
+    smp.interval = 0.002
+    smp.start()
+    best = 0.0
+    for _ in range(6):
+        g, ms = ctx.measure_fp64_peak()
+        best = max(best, g)
+    smp.stop_flag = True
+    smp.join()
+    term_gps, _ = ctx.measure_term_peak()
+    clk = smp.summary()
+    sm_count = 148
+    nominal = 64.0 * sm_count * (clk["sm_max_mhz"] or 1965) * 1e6 / 1e9
+    return {"fp64_ginstr_per_s": best, "fp64_tflops": 2.0 * best / 1e3, "sm_mhz_during_burst": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"],
+            "nominal_ginstr_per_s": nominal, "frac_of_nominal": best / nominal,
+            "how": "ah_measure_fp64_peak: dependent-free DFMA burst (8 chains/thread, 512 threads, 4 CTAs/SM, 2^15 iterations), best of 18, "
+                   "CUDA events; nominal = 64 FP64 lanes x 148 SMs x max SM clock; MEASURED_PEAKS.json carries no FP64 entry",
+            "term_burst_gterms_per_s": term_gps}
+
+
+def timed_steps(torch, dist, dev, steps, fn, barrier):
+    """exactly `steps` calls of fn between two CUDA events on the current stream; returns (max-over-ranks ms, last result, stats sums)"""
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    acc = {"launches": 0, "kernel_ms": 0.0, "main_kernel_ms": 0.0, "vec_ms": 0.0, "host_pre_ms": 0.0, "host_post_ms": 0.0}
+    res = None
+    for _ in range(steps):
+        res = fn()
+        for key in acc:
+            acc[key] += res.stats[key]
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    barrier()
+    t = torch.tensor([ms, float(acc["launches"])], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        return float(tm[0]), res, acc, int(ts[1])
+    return ms, res, acc, acc["launches"]
+
+
+def roofline_of(P, res, acc, steps, cnt, fp64, peaks, world):
+    """k_bisect (round 0 + the Remedy-3 round): 7 FP64-pipe lane-instructions per secular term x steps_k x N / its device time"""
+    fast = (res.status & 0xff) == 0            # (k_full's few eigenpairs are included: their first bisection ran in k_bisect)
+    terms = float(res.steps[fast].astype(np.float64).sum()) * P.npoles
+    t_main = acc["main_kernel_ms"] / steps * 1e-3
+    instr_rate = FP64_INSTR_PER_TERM * terms / t_main / 1e9
+    achieved_tf, peak_tf = 2.0 * instr_rate / 1e3, fp64["fp64_tflops"]
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_achieved = cnt * P.vec_bytes / (acc["vec_ms"] / steps * 1e-3) / 1e9
+    traffic = ncu_pipe = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get(f"{P.kind}_n{P.n}") or (tj if (P.kind == "symarrow" and P.n == tj.get("n")) else None)
+        if ent and world == 1:
+            traffic = ent["k_bisect_round0"]["dram_bytes_per_launch"]
+            ncu_pipe = ent["k_bisect_round0"].get("sm__inst_executed_pipe_fp64")
+    except Exception:
+        pass
+    return {
+        "bound": "fp64", "kernel": f"k_bisect<{P.kind}> (round 0 + Remedy-3 round 1)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf, "traffic": traffic,
+        "peak_source": {"fp64_tflops": peak_tf, "measured": fp64, "ncu_sm__inst_executed_pipe_fp64_per_launch": ncu_pipe,
+                        "ncu_file": "profiles/r2_*_full_*.md (same build; per-launch FP64-pipe instruction count = 7 x terms / 32 lanes + boundary code)"},
+        "how": "FP64-pipe lane-instructions x2 (FMA-equivalent); 7 per secular term x steps_k x N terms per eigenpair / device time of "
+               "k_bisect (round 0 + the Remedy-3 round, CUDA events on their streams inside the timed region); peak = DFMA burst measured "
+               "live in this run (peak_source.measured)",
+        "terms_per_launch": terms, "kernel_ms": t_main * 1e3, "fast_eigenpairs": int(res.stats["n_fast"]),
+        "term_burst": {"gterms_per_s": fp64["term_burst_gterms_per_s"], "achieved_gterms_per_s": terms / t_main / 1e9,
+                       "frac": terms / t_main / 1e9 / fp64["term_burst_gterms_per_s"],
+                       "what": "secular terms/s of the same 7 FP64 + 1 MUFU.RCP64H mix from registers only (no tiles, no sweep "
+                               "boundaries): what the ring, the barriers and the work distribution cost"},
+        "hbm_store": {"kernel": "k_vec", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+    }
+
+
+def numa_local_pinned(torch, local_rank, shape):
+    """pinned host buffer whose pages are first touched by a thread bound to the GPU's NUMA node (cudaHostRegister of
+    first-touched memory): eight ranks then do not all stream their D2H copies into the memory of one socket."""
+    info = {"numa_node": None, "how": "torch pin_memory (no NUMA binding)"}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(physical_gpu_index(local_rank))
+        node = None
+        try:
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            path = f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node"
+            node = int(open(path).read().strip())
+        except Exception:
+            node = None
+        if node is not None and node >= 0:
+            cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+            ids = []
+            for part in cpus.split(","):
+                lo, _, hi = part.partition("-")
+                ids += list(range(int(lo), int(hi or lo) + 1))
+            allowed = sorted(set(ids) & os.sched_getaffinity(0))
+            if allowed:
+                old = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, allowed)
+                try:
+                    t = torch.empty(shape, dtype=torch.float64)
+                    t.zero_()                                  # first touch on the GPU's node
+                    torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * 8, 0)
+                finally:
+                    os.sched_setaffinity(0, old)
+                info = {"numa_node": node, "how": "first-touched by a thread bound to the GPU's NUMA node, then cudaHostRegister"}
+                return t, info
+    except Exception as e:                                     # fall through to the plain pinned allocation
+        info["fallback_reason"] = f"{type(e).__name__}: {e}"[:120]
+    return torch.empty(shape, dtype=torch.float64, pin_memory=True), info
+
+
 def run_ours(args):
     import torch
     import arrowhead_b200 as ab
@@ -177,108 +361,61 @@ def run_ours(args):
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 
     n = args.n
-    D, z, a = gen_symarrow(n)
+    P = Problem(args.workload, n)
     k0, k1 = ab.k_partition(n, world, rank)
     cnt = k1 - k0 + 1
-    U = torch.empty((cnt, n), dtype=torch.float64, device=dev)          # this rank's columns of U (column-major block)
-    flush = torch.empty(32 << 20, dtype=torch.float64, device=dev)      # 256 MB > 126 MB L2 (float64: torch's 1-byte fill kernel is 10x slower than the memory)
+    # this rank's FULL-size U (n x n, column-major: row c of the tensor = column c): the rank fills its own column block in
+    # place, so that the optional all-gather (ah_allgather_columns) needs no staging copy.  n = 32768: 8.6 GB per GPU.
+    full_u = world > 1 and not args.no_allgather and n * n * 8 <= 40e9
+    Ufull = torch.empty((n if full_u else cnt, n), dtype=torch.float64, device=dev)
+    U = Ufull[k0 - 1:k1] if full_u else Ufull
+    V = torch.empty((cnt, n), dtype=torch.float64, device=dev) if P.kind == "halfarrow" else None
+    Uptr, Vptr = U.data_ptr(), (V.data_ptr() if V is not None else None)
+    flush = torch.empty(20 << 20, dtype=torch.float64, device=dev)      # 160 MB > 126 MB L2 (float64: torch's 1-byte fill kernel is 10x slower)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def upload_and_step():       # the drop-in call: validates, pads and uploads D, z, then solves
+    def step():                  # `value`: THE DROP-IN CALL -- host D, z in (validated, padded, uploaded every step), U resident
         flush.zero_()
-        return ctx.symarrow(D, z, a, k0=k0, k1=k1, vectors=False, U_dev=U.data_ptr(), ldu=n)
+        return P.solve(ctx, k0, k1, Uptr, Vptr)
 
-    def step():                  # `value`: inputs already resident in HBM (ah_resolve); `e2e` below uploads them every step
+    def step_resident():         # beside it: inputs already resident in HBM (ah_resolve: launches + per-k results only)
         flush.zero_()
-        return ctx.resolve(k0, k1, vectors=False, U_dev=U.data_ptr(), ldu=n)
+        return P.resolve(ctx, k0, k1, Uptr, Vptr)
 
-    fp64_ginstr, _ = ctx.measure_fp64_peak()
-    term_gps, _ = ctx.measure_term_peak()      # the inner block's instruction mix from registers only
-    res = upload_and_step()
-    for _ in range(max(args.warmup, 3)):
+    fp64 = fp64_denominator(ctx, physical_gpu_index(local_rank))
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         res = step()
     sampler = ClockSampler(physical_gpu_index(local_rank))
-    barrier()
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    launches = 0
-    kern_ms = main_ms = vec_ms = 0.0
-    for _ in range(args.steps):
-        res = step()
-        launches += res.stats["launches"]
-        kern_ms += res.stats["kernel_ms"]
-        main_ms += res.stats["main_kernel_ms"]
-        vec_ms += res.stats["vec_ms"]
-    ev1.record()
-    torch.cuda.synchronize()
+    ms_max, res, acc, launches_all = timed_steps(torch, dist, dev, args.steps, step, barrier)
     sampler.stop_flag = True
-    ms = ev0.elapsed_time(ev1)
-    barrier()
-    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        tm = t.clone()
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ts = t.clone()
-        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        ms_max, launches_all = float(tm[0]), int(ts[1])
-    else:
-        ms_max, launches_all = ms, launches
     value = n * args.steps / (ms_max * 1e-3)
+    rsteps = max(3, min(args.steps, 10))
+    ms_res, _, acc_res, _ = timed_steps(torch, dist, dev, rsteps, step_resident, barrier)
 
-    # ---- roofline of the dominant kernel (k_bisect) on this rank, from the same timed region
-    N = n - 1
-    fast = (res.status & 0xff) == 0            # (k_full's few eigenpairs are included: their first bisection ran in k_bisect)
-    n_fast = res.stats["n_fast"]
-    terms_fast = float(res.steps[fast].astype(np.float64).sum()) * N   # k_bisect (both rounds): one sweep of N secular terms per bisection step
-    t_main = main_ms / args.steps * 1e-3
-    instr_rate = FP64_INSTR_PER_TERM * terms_fast / t_main / 1e9       # G lane-instructions/s
-    achieved_tf = 2.0 * instr_rate / 1e3
-    peak_tf = 2.0 * fp64_ginstr / 1e3
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_achieved = cnt * n * 8 / (vec_ms / args.steps * 1e-3) / 1e9    # U is written by k_vec (its span also hosts the Remedy-3 round)
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj["k_bisect_round0"]["dram_bytes_per_launch"] if n == tj.get("n") and world == 1 else None
-    except Exception:
-        pass
-    roofline = {
-        "bound": "fp64", "kernel": "k_bisect<SymArrow> (round 0 + Remedy-3 round 1)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": achieved_tf / peak_tf, "traffic": traffic,
-        "how": "FP64-pipe lane-instructions x2 (FMA-equivalent); 7 per secular term x steps_k x N terms per "
-               "eigenpair / device time of k_bisect (round 0 + the Remedy-3 round, CUDA events on their streams inside "
-               "the timed region); peak = dependent-free DFMA burst measured live (MEASURED_PEAKS.json has no FP64 entry)",
-        "terms_per_launch": terms_fast, "kernel_ms": t_main * 1e3, "fast_eigenpairs": int(n_fast),
-        "term_burst": {"gterms_per_s": term_gps, "achieved_gterms_per_s": terms_fast / t_main / 1e9,
-                       "frac": terms_fast / t_main / 1e9 / term_gps,
-                       "what": "secular terms/s of the same 7 FP64 + 1 MUFU.RCP64H mix from registers only (no tiles, no sweep "
-                               "boundaries): what the ring, the barriers and the work distribution cost"},
-        "hbm_store": {"kernel": "k_vec", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-    }
+    roofline = roofline_of(P, res, acc, args.steps, cnt, fp64, peaks, world)
 
     # ---- end to end: host D,z in, eigenvalues + Info + this rank's eigenvectors out to pinned host memory
     e2e = None
-    if not args.no_e2e:
-        Uh = torch.empty((cnt, n), dtype=torch.float64, pin_memory=True)
-        Dp = torch.from_numpy(D).pin_memory().numpy()
-        zp = torch.from_numpy(z).pin_memory().numpy()
+    if not args.no_e2e and P.kind != "halfarrow":
+        Uh, numa = numa_local_pinned(torch, local_rank, (cnt, n))
+        Dp = torch.from_numpy(P.D).pin_memory().numpy()
+        zp = torch.from_numpy(P.z).pin_memory().numpy()
         e2e_steps = max(2, min(args.steps, 5))
-
-        if world == 1:
+        if world == 1 and P.kind == "symarrow":
             # the call a user makes: eigen(SymArrow) of the reference API (sort, deflation tests, solve, back-permutation),
             # eigenvectors streamed into a caller-owned pinned buffer
-            A_user = ab.SymArrow(Dp, zp, a, n)
+            A_user = ab.SymArrow(Dp, zp, P.a, n)
             Uh_np = Uh.numpy().T           # the same pinned memory seen as a Fortran-ordered n x n array
 
             class _R:                      # adapter: same fields as the k-range result used below
@@ -290,7 +427,7 @@ def run_ours(args):
                 return r
         else:
             def step_e2e():
-                return ctx.symarrow(Dp, zp, a, k0=k0, k1=k1, vectors=False, U_host=Uh.data_ptr(), ldu=n)
+                return P.solve(ctx, k0, k1, Uh.data_ptr(), host=True, D=Dp, z=zp)
 
         r2 = step_e2e()
         barrier()
@@ -299,63 +436,111 @@ def run_ours(args):
             r2 = step_e2e()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        mine = float(r2.stats["d2h_bytes"]) * e2e_steps / dt / 1e9
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        rates = torch.zeros(world, dtype=torch.float64, device=dev); rates[rank] = mine
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(rates, op=dist.ReduceOp.SUM)
         barrier()
         hb = torch.tensor([float(r2.stats["h2d_bytes"]), float(r2.stats["d2h_bytes"])], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(hb, op=dist.ReduceOp.SUM)
         e2e = {"value": n * e2e_steps / float(tt[0]), "unit": "eigenpairs/s", "h2d_bytes_per_step": int(hb[0]),
                "d2h_bytes_per_step": int(hb[1]), "steps": e2e_steps,
+               "d2h_gb_per_s_per_rank": [round(float(x), 2) for x in rates.cpu()], "pinned_buffer_rank0": numa,
                "what": ("eigen(SymArrow) of the Python mirror of the reference API (host sort + deflation tests + C-ABI solve + "
-                        "permutation check), host D,z in, U/lambda/Info out to pinned host memory (wall clock)") if world == 1 else
-                       "ah_symarrow_eigen per rank with host D,z and this rank's U block/lambda/Info copied to pinned host memory (wall clock)"}
+                        "permutation check), host D,z in, U/lambda/Info out to pinned host memory (wall clock)") if (world == 1 and P.kind == "symarrow") else
+                       f"{P.entry} per rank with host D,z and this rank's U block/lambda/Info copied to pinned host memory (wall clock)"}
         # spot-check: the host copy equals the resident result
         assert np.array_equal(r2.lam, res.lam)
         assert torch.equal(Uh[cnt // 2].to(dev), U[cnt // 2])
+        if "numa_node" in numa and numa["numa_node"] is not None:
+            torch.cuda.cudart().cudaHostUnregister(Uh.data_ptr())
+        del Uh
 
-    allgather_ms = None
-    if dist is not None and args.allgather:
-        # optional, outside the headline: every rank ends up with all of U (NCCL all_gather of the column blocks)
-        from arrowhead_b200.sharding import allgather_columns
+    # ---- all-gather of U over NVLink through the C ABI (north_star: only when the caller needs U on one device;
+    # reported beside the headline, never inside it).  Every rank ends up with all n x n entries.
+    allgather = None
+    if dist is not None and full_u:
+        uid = [ctx.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.nccl_init(world, rank, uid[0])
         barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        Ufull = allgather_columns(U, n, n, world, rank, dist)
-        a1.record()
-        torch.cuda.synchronize()
-        tt = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+        ctx.allgather_columns(Ufull.data_ptr(), n, n)                    # warm-up (NCCL channel setup)
+        barrier()
+        ms_ag = ctx.allgather_columns(Ufull.data_ptr(), n, n)
+        tt = torch.tensor([ms_ag], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        allgather_ms = float(tt[0])
-        assert Ufull.shape == (n, n) and torch.equal(Ufull[k0 - 1:k1], U)
-        del Ufull
+        # every rank now holds every column: compare a few foreign columns with their owners' copies
+        probe = torch.stack([Ufull[(r * n) // world + 3] for r in range(world)])
+        ref = probe.clone()
+        dist.broadcast(ref, src=0)
+        same = bool(torch.equal(ref, probe))
+        ok = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        recv_bytes = (n - cnt) * n * 8
+        allgather = {"ms": float(tt[0]), "api": "ah_nccl_init + ah_allgather_columns (ncclAllGather in place, libnccl dlopen'ed by the library)",
+                     "bytes_received_per_rank": recv_bytes, "gb_per_s_per_rank": recv_bytes / (float(tt[0]) * 1e-3) / 1e9,
+                     "all_ranks_hold_identical_U": bool(ok.item() == 1.0)}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and P.kind == "symarrow":
         threads = host_threads()
-        sample, _ = cpu_sample_size(n, D, z, a, threads, 12.0)
-        rate, dt, kr = time_oracle(n, D, z, a, sample, threads)
+        sample, _ = cpu_sample_size(n, P.D, P.z, P.a, threads, 12.0)
+        rate, dt, kr = time_oracle(n, P.D, P.z, P.a, sample, threads)
         cpu = {"value": rate, "unit": "eigenpairs/s", "cores": threads, "kind": "port",
                "sample": f"{sample} consecutive eigenpairs k={kr[0]}..{kr[1]} of the same n={n} problem, {dt:.1f} s, "
                          "oracle/arrowhead_oracle.c with OpenMP static over k"}
 
+    # ---- the north-star target size as a sub-record of the default run (1 GPU, SymArrow): n = 65536, 3 steps
+    target = None
+    if world == 1 and P.kind == "symarrow" and n == 32768 and not args.no_target:
+        try:
+            del Ufull, U
+            torch.cuda.empty_cache()
+            nt = 65536
+            Pt = Problem("symarrow", nt)
+            Ut = torch.empty((nt, nt), dtype=torch.float64, device=dev)      # 34.4 GB resident
+            def step_t():
+                flush.zero_()
+                return Pt.solve(ctx, 1, nt, Ut.data_ptr())
+            for _ in range(2):
+                rt = step_t()
+            ms_t, rt, acc_t, _ = timed_steps(torch, None, dev, 3, step_t, barrier)
+            rl = roofline_of(Pt, rt, acc_t, 3, nt, fp64, peaks, 1)
+            lam = rt.lam
+            target = {"workload": Pt.workload, "value": nt * 3 / (ms_t * 1e-3), "unit": "eigenpairs/s", "ms_per_step": ms_t / 3, "steps": 3,
+                      "roofline_frac": rl["frac"], "k_bisect_ms": rl["kernel_ms"], "achieved_tflops": rl["achieved"],
+                      "hbm_store_frac": rl["hbm_store"]["frac"],
+                      "checks": {"strictly_descending": bool(np.all(np.diff(lam) < 0)),
+                                 "interlacing": bool(np.all(lam[1:] < Pt.D) and np.all(lam[:-1] > Pt.D)),
+                                 "trace_rel_err": float(abs(lam.sum() - (Pt.D.sum() + Pt.a)) / np.abs(lam).sum()),
+                                 "status_all_ok": bool(((rt.status & 0xff) == 0).all())}}
+            del Ut
+        except Exception as e:                                               # never lose the headline line to the sub-record
+            target = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     if rank == 0:
         line = {
-            "metric": METRIC % n, "value": value, "unit": "eigenpairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "metric": P.metric, "value": value, "unit": "eigenpairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"SymArrow n={n} full eigen(), GenSymArrow-like rng(421), ordered, arrow top last",
+            "config": {"workload": P.workload,
                        "parallelism": f"k-range x{world}", "U": "device-resident, column blocks per rank",
-                       "inputs": "D, z (0.5 MB) resident in HBM, uploaded once before the timed region (ah_resolve); e2e uploads them every step",
-                       "l2": "256 MB flush write before every step; the step itself streams out n^2*8 bytes >> L2",
-                       "allgather_U_ms": allgather_ms,
-                       "kernel_ms_per_step_rank0": kern_ms / args.steps,
+                       "timed_call": f"{P.entry} (the drop-in boundary call: host D, z validated, padded and uploaded every step; "
+                                     "per-k results back to the host; eigenvectors stay in HBM)",
+                       "value_resident_inputs": {"value": n * rsteps / (ms_res * 1e-3), "ms_per_step": ms_res / rsteps, "steps": rsteps,
+                                                 "what": "the same step through ah_resolve (D, z already resident in HBM: no validation, padding, upload)"},
+                       "l2": "160 MB flush write before every step (inside the timed region); the step itself streams out n^2*8 bytes >> L2",
+                       "allgather_U": allgather, "allgather_U_ms": allgather["ms"] if allgather else None,
+                       "kernel_ms_per_step_rank0": acc["kernel_ms"] / args.steps,
+                       "host_ms_per_step_rank0": {"before_first_launch": acc["host_pre_ms"] / args.steps, "after_sync": acc["host_post_ms"] / args.steps},
                        "kernel_ms_breakdown_rank0": {k: res.stats[k] for k in ("prep_ms", "bisect_ms", "rem3_ms", "vec_ms", "full_ms")},
                        "n_full_rank0": int(res.stats["n_full"]), "n_rem3_rank0": int(res.stats["n_rem3"]),
                        "total_steps_rank0": int(res.stats["total_steps"])},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "target_n65536": target,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -366,7 +551,7 @@ def run_tdc(args):
     """Secondary workload (BASELINE.json configs[4]): tdc() of a SymTridiagonal, device-resident
     level-batched path vs the oracle's restatement of arrowhead7.jl:10-36 on the host cores.  Not the headline metric."""
     import arrowhead_b200 as ab
-    n = args.n if args.n != 32768 else 8192
+    n = args.n
     rng = np.random.default_rng(421)
     dv, ev = 2.0 + 1e-3 * rng.standard_normal(n), -1.0 + 1e-3 * rng.standard_normal(n - 1)
     ab.build_library()
@@ -394,19 +579,26 @@ def run_tdc(args):
                       "cpu_baseline": cpu}), flush=True)
 
 
+DEFAULT_N = {"symarrow": 32768, "symdpr1": 16384, "halfarrow": 16384, "tdc": 8192}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", "--size", dest="n", type=int, default=32768,
+    ap.add_argument("--n", "--size", dest="n", type=int, default=None,
                     help="matrix order (under torchrun spell it --size: its own parser treats --n as an abbreviation)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="symarrow", choices=["symarrow", "tdc"])
-    ap.add_argument("--allgather", action="store_true", help="N>1: also time an NCCL all-gather of U (reported separately)")
+    ap.add_argument("--workload", default="symarrow", choices=["symarrow", "symdpr1", "halfarrow", "tdc"])
+    ap.add_argument("--no-allgather", action="store_true", help="N>1: skip the NCCL all-gather of U (timed after the headline, reported in config)")
+    ap.add_argument("--allgather", action="store_true", help="(kept for compatibility: the all-gather now always runs at N>1)")
+    ap.add_argument("--no-target", action="store_true", help="skip the n=65536 sub-record of the default 1-GPU run")
     args = ap.parse_args()
+    if args.n is None:
+        args.n = DEFAULT_N[args.workload]
     if args.workload == "tdc":
         run_tdc(args)
     elif args.impl == "reference":
