@@ -206,8 +206,10 @@ class Context:
 
     # ---- the three hot-path entry points ---------------------------------------------------------
     def _run(self, fn, args, k0, k1, nrows_u, nrows_v, vectors, U_dev, ldu, V_dev, ldv, rowmap_u, rowmap_v,
-             rowscale_v, U_host=None, V_host=None):
-        res = RangeResult(k0, k1)
+             rowscale_v, U_host=None, V_host=None, into=None):
+        # `into`: a RangeResult of the same k-range to fill again (callers that solve repeatedly avoid fresh pages for
+        # the nine per-k arrays: at n = 32768 first-touch page faults cost 0.2 ms per call)
+        res = into if (into is not None and into.k0 == k0 and into.k1 == k1) else RangeResult(k0, k1)
         r = AhResult()
         res.fill(r)
         cnt = k1 - k0 + 1
@@ -238,43 +240,43 @@ class Context:
         res.stats = self.stats()
         return res
 
-    def symarrow(self, D, z, a, tau=None, k0=1, k1=None, vectors=True, U_dev=None, ldu=0, rowmap=None, U_host=None):
+    def symarrow(self, D, z, a, tau=None, k0=1, k1=None, vectors=True, U_dev=None, ldu=0, rowmap=None, U_host=None, into=None):
         D = np.ascontiguousarray(D, np.float64); z = np.ascontiguousarray(z, np.float64)
         tau_a = None if tau is None else np.ascontiguousarray(tau, np.float64)
         N = D.size
         k1 = N + 1 if k1 is None else k1
         args = (C.c_int64(N), _ptr(D, _dp), _ptr(z, _dp), C.c_double(float(a)), _ptr(tau_a, _dp))
         return self._run(self.lib.ah_symarrow_eigen, args, k0, k1, N + 1, 0, vectors, U_dev, ldu, None, 0, rowmap, None,
-                         None, U_host=U_host)
+                         None, U_host=U_host, into=into)
 
     def resolve(self, k0, k1, vectors=True, U_dev=None, ldu=0, V_dev=None, ldv=0, rowmap_u=None, rowmap_v=None,
-                rowscale_v=None, U_host=None):
+                rowscale_v=None, U_host=None, into=None):
         """ah_resolve: another k-range of the problem of the last symarrow / symdpr1 / halfarrow call on this context
         (inputs still resident on the device: no validation, padding or host->device copy)."""
         if getattr(self, "_resident", None) is None:
             raise ArrowheadError(-1, "resolve(): no solve on this context yet")
         nrows_u, nrows_v = self._resident
         return self._run(self.lib.ah_resolve, (), k0, k1, nrows_u, nrows_v, vectors, U_dev, ldu, V_dev, ldv, rowmap_u,
-                         rowmap_v, rowscale_v, U_host=U_host)
+                         rowmap_v, rowscale_v, U_host=U_host, into=into)
 
-    def symdpr1(self, D, u, rho, tau=None, k0=1, k1=None, vectors=True, U_dev=None, ldu=0, rowmap=None, U_host=None):
+    def symdpr1(self, D, u, rho, tau=None, k0=1, k1=None, vectors=True, U_dev=None, ldu=0, rowmap=None, U_host=None, into=None):
         D = np.ascontiguousarray(D, np.float64); u = np.ascontiguousarray(u, np.float64)
         tau_a = None if tau is None else np.ascontiguousarray(tau, np.float64)
         n = D.size
         k1 = n if k1 is None else k1
         args = (C.c_int64(n), _ptr(D, _dp), _ptr(u, _dp), C.c_double(float(rho)), _ptr(tau_a, _dp))
         return self._run(self.lib.ah_symdpr1_eigen, args, k0, k1, n, 0, vectors, U_dev, ldu, None, 0, rowmap, None, None,
-                         U_host=U_host)
+                         U_host=U_host, into=into)
 
     def halfarrow(self, D, z, tau=None, k0=1, k1=None, vectors=True, U_dev=None, ldu=0, V_dev=None, ldv=0,
-                  rowmap_u=None, rowmap_v=None, rowscale_v=None):
+                  rowmap_u=None, rowmap_v=None, rowscale_v=None, into=None):
         D = np.ascontiguousarray(D, np.float64); z = np.ascontiguousarray(z, np.float64)
         tau_a = None if tau is None else np.ascontiguousarray(tau, np.float64)
         nd, nz = D.size, z.size
         k1 = nz if k1 is None else k1
         args = (C.c_int64(nd), C.c_int64(nz), _ptr(D, _dp), _ptr(z, _dp), _ptr(tau_a, _dp))
         return self._run(self.lib.ah_halfarrow_svd, args, k0, k1, nz, nd + 1, vectors, U_dev, ldu, V_dev, ldv, rowmap_u,
-                         rowmap_v, rowscale_v)
+                         rowmap_v, rowscale_v, into=into)
 
     def symarrow_eigvals_dd(self, D, z, zlo, a, alo, tau, k0=1, k1=None):
         """eigenvalues only, double-double border (z+zlo, a+alo): rootsah's per-k solver (arrowhead7.jl:351-495)"""

@@ -368,7 +368,11 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         if (ctx->mode == 0) {
             KState *ks = (KState *)ctx->dKs.p;
             int64_t *rlist = (int64_t *)ctx->dRList.p;
+#ifdef AH_DIAG_TIMING
+            AH_CUDA(cudaMemsetAsync(dcount, 0, 2048, st));
+#else
             AH_CUDA(cudaMemsetAsync(dcount, 0, 128 + 256 * 4, st));
+#endif
             rc = ah::launch_prep(L.kind, P, ks, kb, cc, dlist, dcount, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_prep launch");
             AH_CUDA(cudaEventRecord(E[1], st));
@@ -468,6 +472,17 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         }
     }
 
+#ifdef AH_DIAG_TIMING
+    {
+        unsigned long long tg[8];
+        AH_CUDA(cudaMemcpyAsync(tg, (unsigned long long *)ctx->dCount.p + 152, sizeof tg, cudaMemcpyDeviceToHost, st));
+        AH_CUDA(cudaStreamSynchronize(st));
+        const double ctas = (double)std::max<unsigned long long>(1, tg[7]), sw = (double)std::max<unsigned long long>(1, tg[6]);
+        fprintf(stderr, "[diag] k_bisect warp 0, cycles per sweep (mean over %llu CTAs, %.1f sweeps each): boundary %.0f | barrier2 wait %.0f | "
+                        "param copy %.0f | tiles %.0f | reduce %.0f | barrier1 wait %.0f\n", tg[7], sw / ctas, tg[0] / sw, tg[1] / sw, tg[2] / sw,
+                tg[3] / sw, tg[4] / sw, tg[5] / sw);
+    }
+#endif
     // ---- per-k outputs -> host
     AH_CUDA(cudaEventRecord(ctx->ev[6], st));
     if ((rc = ensure_pinned(ctx, out_bytes(cnt)))) return rc;
@@ -1155,7 +1170,9 @@ int ah_measure_fp64_peak(ah_ctx *ctx, double *ginstr_per_s, double *elapsed_ms) 
 int ah_measure_term_peak(ah_ctx *ctx, double *gterms_per_s, double *elapsed_ms) {
     if (!ctx || !gterms_per_s) return AH_ERR_INVALID_ARG;
     AH_CUDA(cudaSetDevice(ctx->device));
-    const int threads = 256, blocks = ctx->sm_count * 2, iters = 1 << 13;
+    int blocks = ctx->sm_count * 2;
+    if (const char *e = getenv("ARROWHEAD_B200_BURST_CTAS")) blocks = ctx->sm_count * std::max(1, atoi(e));   // experiment: 1 CTA (8 warps) per SM alone
+    const int threads = 256, iters = 1 << 13;
     int rc;
     if ((rc = ensure(ctx, ctx->dStage[0], (size_t)threads * blocks * 8))) return rc;
     double *o = (double *)ctx->dStage[0].p;

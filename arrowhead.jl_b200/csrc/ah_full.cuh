@@ -142,6 +142,7 @@ __device__ void inv_at_value(const Problem &P, double sig, double tol, InvValue 
     const double *__restrict__ W = P.w;
     double Ps = 0.0, Qs = 0.0, uu = 0.0, mabs = 0.0;
     double mx1 = -INFINITY, mx2 = -INFINITY, mn1 = INFINITY, mn2 = INFINITY;
+#pragma unroll 4
     for (int64_t l = threadIdx.x; l < N; l += BT) {
         double w = W[l];
         double D1 = __ddiv_rn(1.0, dshift<KIND>(D[l], sig));

@@ -522,8 +522,16 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
     };
     if (tid == 0) { for (; g_issue < (uint32_t)(BS - 1); ++g_issue) issue_tile(g_issue); }
 
+#ifdef AH_DIAG_TIMING
+    // diagnostic build only: where warp 0 spends its cycles (clock64 deltas summed per CTA, atomically added to dcount[152..159])
+    long long tg_boundary = 0, tg_b2 = 0, tg_param = 0, tg_tiles = 0, tg_reduce = 0, tg_b1 = 0, tg_sweeps = 0, tg_mark = clock64();
+#define AH_TG(var) do { if (tid == 0) { const long long now__ = clock64(); var += now__ - tg_mark; tg_mark = now__; } } while (0)
+#else
+#define AH_TG(var) do { } while (0)
+#endif
     bool first = true;
     while (true) {
+        AH_TG(tg_b1);
         // ================= sweep boundary: warp j advances slot j =================
         if (warp < NSLOT) {
             BSlot &S = sh.slot[warp];
@@ -669,7 +677,9 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             }
         }
         first = false;
+        AH_TG(tg_boundary);
         __syncthreads();
+        AH_TG(tg_b2);
 
         // ================= per-thread copies of the sweep parameters =================
         unsigned actmask = 0;
@@ -697,6 +707,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         double acc[NSLOT];
 #pragma unroll
         for (int j = 0; j < NSLOT; ++j) acc[j] = 0.0;
+        AH_TG(tg_param);
 
         // ================= the sweep =================
         for (int tile = 0; tile < ntiles; ++tile, ++g) {
@@ -759,14 +770,27 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             }
         }
 
+        AH_TG(tg_tiles);
         // ================= reduce this sweep's partial sums =================
 #pragma unroll
         for (int j = 0; j < NSLOT; ++j) {
             const double v = warp_allreduce(acc[j], OpSum());
             if (lane == 0) sh.part[j][warp] = v;
         }
+        AH_TG(tg_reduce);
+#ifdef AH_DIAG_TIMING
+        if (tid == 0) ++tg_sweeps;
+#endif
         __syncthreads();
     }
+#ifdef AH_DIAG_TIMING
+    if (tid == 0 && ROUND == 0) {
+        atomicAdd(dcount + 152, (unsigned long long)tg_boundary); atomicAdd(dcount + 153, (unsigned long long)tg_b2);
+        atomicAdd(dcount + 154, (unsigned long long)tg_param); atomicAdd(dcount + 155, (unsigned long long)tg_tiles);
+        atomicAdd(dcount + 156, (unsigned long long)tg_reduce); atomicAdd(dcount + 157, (unsigned long long)tg_b1);
+        atomicAdd(dcount + 158, (unsigned long long)tg_sweeps); atomicAdd(dcount + 159, 1ull);
+    }
+#endif
 
     // drain the prefetched tiles before the CTA (and its shared memory) goes away
     if (tid == 0) {
@@ -851,15 +875,38 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
             int par = 0;
             bool nanfail = false;
             while (!bisect_converged(S)) {
+                // One CTA per eigenpair: a sweep is latency-bound on the L2 loads unless several tiles are in flight.  The
+                // loads of RU tiles are issued together and the next group is fetched while this one is evaluated; the
+                // terms are still accumulated tile by tile, pair by pair -- k_bisect's order, bit for bit.
+                constexpr int RU = 4, RH = BE / 2;
                 double acc = 0.0;
-                for (int tile = 0; tile < ntiles; ++tile) {
-                    const double *Dt = P.D + (int64_t)tile * BTL, *Wt = P.w2 + (int64_t)tile * BTL;
+                double2 dcur[RU][RH], wcur[RU][RH], dnxt[RU][RH], wnxt[RU][RH];
+                auto fetch = [&](int tile0, double2 (&dd)[RU][RH], double2 (&ww)[RU][RH]) {
 #pragma unroll
-                    for (int e = 0; e < BE; e += 2) {
-                        const double2 d2 = ldg2(Dt + elem_offset(tid, e)), w2 = ldg2(Wt + elem_offset(tid, e));
-                        acc = secular_term_acc(acc, dshift<KIND>(d2.x, S.sigma), S.m, w2.x);
-                        acc = secular_term_acc(acc, dshift<KIND>(d2.y, S.sigma), S.m, w2.y);
+                    for (int u = 0; u < RU; ++u) {
+                        const int tile = min(tile0 + u, ntiles - 1);      // (a clamped tile is loaded but never accumulated)
+                        const double *Dt = P.D + (int64_t)tile * BTL, *Wt = P.w2 + (int64_t)tile * BTL;
+#pragma unroll
+                        for (int h = 0; h < RH; ++h) { dd[u][h] = ldg2(Dt + elem_offset(tid, 2 * h)); ww[u][h] = ldg2(Wt + elem_offset(tid, 2 * h)); }
                     }
+                };
+                fetch(0, dcur, wcur);
+                for (int tile0 = 0; tile0 < ntiles; tile0 += RU) {
+                    if (tile0 + RU < ntiles) fetch(tile0 + RU, dnxt, wnxt);
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) {
+                        if (tile0 + u < ntiles) {
+#pragma unroll
+                            for (int h = 0; h < RH; ++h) {
+                                acc = secular_term_acc(acc, dshift<KIND>(dcur[u][h].x, S.sigma), S.m, wcur[u][h].x);
+                                acc = secular_term_acc(acc, dshift<KIND>(dcur[u][h].y, S.sigma), S.m, wcur[u][h].y);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < RU; ++u)
+#pragma unroll
+                        for (int h = 0; h < RH; ++h) { dcur[u][h] = dnxt[u][h]; wcur[u][h] = wnxt[u][h]; }
                 }
                 const double v = warp_allreduce(acc, OpSum());
                 if (lane == 0) part2[par][warp] = v;
