@@ -52,6 +52,7 @@ EXPORTS = [
     "ah_scale_rows_phase", "ah_symarrow_eigvals_dd", "ah_symarrow_eigen_batched", "ah_gather_elements", "ah_gather_permuted_batched",
     "ah_copy2d_batched", "ah_dgemm_batched",
     "ah_measure_fp64_peak", "ah_measure_term_peak", "ah_measure_store_bw",
+    "ah_set_async", "ah_wait", "ah_last_gemm_ms", "ah_measure_dmma_peak",
     "ah_multi_create", "ah_multi_destroy", "ah_multi_ndev", "ah_multi_ctx", "ah_multi_last_error", "ah_multi_elapsed_ms",
     "ah_k_partition", "ah_multi_symarrow_eigen", "ah_multi_symdpr1_eigen", "ah_multi_halfarrow_svd",
     "ah_multi_allgather_columns", "ah_nccl_unique_id", "ah_nccl_init", "ah_allgather_columns",
@@ -104,6 +105,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ah_copy2d_batched.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, u64p, C.c_int64, u64p, C.c_int64]
     lib.ah_dgemm_batched.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, u64p, C.c_int64, u64p, C.c_int64, u64p, C.c_int64]
     lib.ah_scale_rows_phase.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, _dp, C.c_int, C.c_int64, C.c_int64]
+    lib.ah_set_async.argtypes = [vp, C.c_int]
+    lib.ah_wait.argtypes = [vp]
+    lib.ah_last_gemm_ms.argtypes = [vp, _dp]
+    lib.ah_measure_dmma_peak.argtypes = [vp, _dp, _dp]
     lib.ah_measure_fp64_peak.argtypes = [vp, _dp, _dp]
     lib.ah_measure_term_peak.argtypes = [vp, _dp, _dp]
     lib.ah_measure_store_bw.argtypes = [vp, C.c_int64, _dp]
@@ -380,6 +385,23 @@ class Context:
         ms = C.c_double()
         self._check(self.lib.ah_allgather_columns(self.handle, C.c_void_p(int(U_full_dev)), int(ld), int(kmax), C.byref(ms)))
         return ms.value
+
+    def set_async(self, on: bool):
+        """device utilities enqueue and return (True) or synchronise before returning (False, the default)"""
+        self._check(self.lib.ah_set_async(self.handle, 1 if on else 0))
+
+    def wait(self):
+        self._check(self.lib.ah_wait(self.handle))
+
+    def last_gemm_ms(self) -> float:
+        ms = C.c_double()
+        self._check(self.lib.ah_last_gemm_ms(self.handle, C.byref(ms)))
+        return ms.value
+
+    def measure_dmma_peak(self):
+        g, ms = C.c_double(), C.c_double()
+        self._check(self.lib.ah_measure_dmma_peak(self.handle, C.byref(g), C.byref(ms)))
+        return g.value, ms.value
 
     def measure_fp64_peak(self):
         g, ms = C.c_double(), C.c_double()

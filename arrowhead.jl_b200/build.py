@@ -7,14 +7,14 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 SOURCES = [os.path.join(_PKG, "csrc", "ah_api.cu")]
-HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("ah_device.cuh", "ah_full.cuh", "ah_pipe.cuh", "ah_roots.cuh", "ah_multi.inl")] + [
+HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("ah_device.cuh", "ah_full.cuh", "ah_pipe.cuh", "ah_roots.cuh", "ah_gemm.cuh", "ah_multi.inl")] + [
     os.path.join(os.path.dirname(_PKG), "include", "arrowhead_b200.h")]
 OUT = os.path.join(_PKG, "libarrowhead_b200.so")
 
 # -fmad=false: the only FMAs in the binary are the explicit ones (secular term, two-product), so the
 # rest rounds like the reference's Julia code.  -lineinfo: ncu source pages map to these files.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-lcublas", "-ldl"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-ldl"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

@@ -6,7 +6,6 @@
 // ah_fast.cuh / ah_full.cuh or fails.
 #include "../../include/arrowhead_b200.h"
 
-#include <cublas_v2.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -23,6 +22,7 @@
 #include "ah_full.cuh"
 #include "ah_pipe.cuh"
 #include "ah_roots.cuh"
+#include "ah_gemm.cuh"
 
 namespace {
 
@@ -61,7 +61,9 @@ struct ah_ctx {
     size_t hPinnedCap = 0;
     double *hIn = nullptr;      // pinned staging of the padded inputs D | w | w^2
     size_t hInCap = 0;
-    cublasHandle_t blas = nullptr;       // created on first use (ah_dgemm_batched)
+    bool async_utils = false;            // ah_set_async: the device utilities enqueue and return (ah_wait synchronises)
+    char *hArena = nullptr;              // pinned staging for the small host arrays of the utilities (pointer / index vectors)
+    size_t hArenaCap = 0, hArenaUsed = 0;
     DevBuf dPtrA, dPtrB, dPtrC, dIdx, dBatchA;
     std::vector<cudaEvent_t> chunk_ev;   // 5 timing events per column block of the current call
     unsigned long long *hCounts = nullptr;  // pinned, 2 per column block: hand-over / Remedy-3 counts of the last call
@@ -103,6 +105,37 @@ int ensure_pinned(ah_ctx *ctx, size_t bytes) {
     cudaError_t e = cudaMallocHost(&ctx->hPinned, bytes);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_NOMEM, "cudaMallocHost failed"); }
     ctx->hPinnedCap = bytes;
+    return AH_OK;
+}
+
+// Host arrays of the device utilities go through a pinned arena so that the copy is truly asynchronous (a
+// cudaMemcpyAsync from pageable memory synchronises the stream first).  Slots are recycled at every synchronisation.
+int h2d_staged(ah_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (need > ctx->hArenaCap - ctx->hArenaUsed) {
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_CUDA_BASE, "stream synchronize failed"); }
+        ctx->hArenaUsed = 0;
+        if (need > ctx->hArenaCap) {
+            if (ctx->hArena) cudaFreeHost(ctx->hArena);
+            ctx->hArena = nullptr; ctx->hArenaCap = 0;
+            const size_t cap = std::max<size_t>(need, (size_t)8 << 20);
+            if (cudaMallocHost((void **)&ctx->hArena, cap) != cudaSuccess) { cudaGetLastError(); return fail(ctx, AH_ERR_NOMEM, "cudaMallocHost failed"); }
+            ctx->hArenaCap = cap;
+        }
+    }
+    char *slot = ctx->hArena + ctx->hArenaUsed;
+    ctx->hArenaUsed += need;
+    std::memcpy(slot, src_host, bytes);
+    cudaError_t e = cudaMemcpyAsync(dst_dev, slot, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMemcpyAsync (staged host array)");
+    return AH_OK;
+}
+// end of a device utility: synchronise unless the caller asked for enqueue-only behaviour (ah_set_async)
+int util_done(ah_ctx *ctx) {
+    if (ctx->async_utils) return AH_OK;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    ctx->hArenaUsed = 0;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaStreamSynchronize");
     return AH_OK;
 }
 
@@ -731,7 +764,7 @@ void ah_destroy(ah_ctx *ctx) {
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->ev_stage) if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
-    if (ctx->blas) cublasDestroy(ctx->blas);
+    if (ctx->hArena) cudaFreeHost(ctx->hArena);
     for (DevBuf *b : {&ctx->dPtrA, &ctx->dPtrB, &ctx->dPtrC, &ctx->dIdx, &ctx->dBatchA})
         if (b->p) cudaFree(b->p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -879,16 +912,14 @@ int ah_set_identity(ah_ctx *ctx, double *U_dev, int64_t nrows, int64_t ncols, in
     AH_CUDA(cudaSetDevice(ctx->device));
     k_set_identity<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(U_dev, nrows, ncols, ld);
     AH_CUDA(cudaGetLastError());
-    AH_CUDA(cudaStreamSynchronize(ctx->stream));
-    return AH_OK;
+    return util_done(ctx);
 }
 int ah_apply_givens_rows(ah_ctx *ctx, double *U_dev, int64_t ld, int64_t ncols, int64_t i1, int64_t i2, double c, double s) {
     if (!ctx || !U_dev || ncols < 1 || i1 < 0 || i2 < 0 || i1 >= ld || i2 >= ld || i1 == i2) return AH_ERR_INVALID_ARG;
     AH_CUDA(cudaSetDevice(ctx->device));
     k_givens_rows<<<(int)std::min<int64_t>((ncols + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(U_dev, ld, ncols, i1, i2, c, s);
     AH_CUDA(cudaGetLastError());
-    AH_CUDA(cudaStreamSynchronize(ctx->stream));
-    return AH_OK;
+    return util_done(ctx);
 }
 int ah_gather_permuted(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src,
                        const int64_t *rows, int64_t nrows, const int64_t *cols, int64_t ncols) {
@@ -897,13 +928,12 @@ int ah_gather_permuted(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const doubl
     int rc;
     if ((rc = ensure(ctx, ctx->dMap1, nrows * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dMap2, ncols * 8))) return rc;
-    AH_CUDA(cudaMemcpyAsync(ctx->dMap1.p, rows, nrows * 8, cudaMemcpyHostToDevice, ctx->stream));
-    AH_CUDA(cudaMemcpyAsync(ctx->dMap2.p, cols, ncols * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = h2d_staged(ctx, ctx->dMap1.p, rows, nrows * 8))) return rc;
+    if ((rc = h2d_staged(ctx, ctx->dMap2.p, cols, ncols * 8))) return rc;
     k_gather<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const int64_t *)ctx->dMap1.p, nrows,
                                                           (const int64_t *)ctx->dMap2.p, ncols);
     AH_CUDA(cudaGetLastError());
-    AH_CUDA(cudaStreamSynchronize(ctx->stream));
-    return AH_OK;
+    return util_done(ctx);
 }
 
 int ah_symarrow_eigen_batched(ah_ctx *ctx, int64_t nb, int64_t N, const double *D, const double *z, const double *a,
@@ -1073,13 +1103,12 @@ int ah_gather_permuted_batched(ah_ctx *ctx, int64_t nb, double *dst_dev, int64_t
     int rc;
     if ((rc = ensure(ctx, ctx->dMap1, nb * nrows * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dMap2, nb * ncols * 8))) return rc;
-    AH_CUDA(cudaMemcpyAsync(ctx->dMap1.p, rows, nb * nrows * 8, cudaMemcpyHostToDevice, ctx->stream));
-    AH_CUDA(cudaMemcpyAsync(ctx->dMap2.p, cols, nb * ncols * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = h2d_staged(ctx, ctx->dMap1.p, rows, nb * nrows * 8))) return rc;
+    if ((rc = h2d_staged(ctx, ctx->dMap2.p, cols, nb * ncols * 8))) return rc;
     k_gather_batched<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(dst_dev, dst_stride, ld_dst, src_dev, src_stride, ld_src,
                                                                   (const int64_t *)ctx->dMap1.p, nrows, (const int64_t *)ctx->dMap2.p, ncols, nb);
     AH_CUDA(cudaGetLastError());
-    AH_CUDA(cudaStreamSynchronize(ctx->stream));
-    return AH_OK;
+    return util_done(ctx);
 }
 
 int ah_copy2d_batched(ah_ctx *ctx, int64_t nb, int64_t nrows, int64_t ncols, const uint64_t *dst_ptrs, int64_t ld_dst,
@@ -1089,42 +1118,32 @@ int ah_copy2d_batched(ah_ctx *ctx, int64_t nb, int64_t nrows, int64_t ncols, con
     int rc;
     if ((rc = ensure(ctx, ctx->dPtrA, nb * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dPtrC, nb * 8))) return rc;
-    AH_CUDA(cudaMemcpyAsync(ctx->dPtrA.p, src_ptrs, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
-    AH_CUDA(cudaMemcpyAsync(ctx->dPtrC.p, dst_ptrs, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = h2d_staged(ctx, ctx->dPtrA.p, src_ptrs, nb * 8))) return rc;
+    if ((rc = h2d_staged(ctx, ctx->dPtrC.p, dst_ptrs, nb * 8))) return rc;
     k_copy2d_batched<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const uint64_t *)ctx->dPtrC.p, ld_dst, (const uint64_t *)ctx->dPtrA.p, ld_src,
                                                                   nrows, ncols, nb);
     AH_CUDA(cudaGetLastError());
-    AH_CUDA(cudaStreamSynchronize(ctx->stream));
-    return AH_OK;
+    return util_done(ctx);
 }
 
 int ah_dgemm_batched(ah_ctx *ctx, int64_t nb, int64_t m, int64_t n, int64_t k, const uint64_t *A_ptrs, int64_t lda,
                      const uint64_t *B_ptrs, int64_t ldb, const uint64_t *C_ptrs, int64_t ldc) {
     if (!ctx || !A_ptrs || !B_ptrs || !C_ptrs || nb < 1 || m < 1 || n < 1 || k < 1 || lda < m || ldb < k || ldc < m) return AH_ERR_INVALID_ARG;
+    if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX || nb > 65535) return fail(ctx, AH_ERR_INVALID_ARG, "ah_dgemm_batched: dimension too large");
     AH_CUDA(cudaSetDevice(ctx->device));
-    if (!ctx->blas) {
-        if (cublasCreate(&ctx->blas) != CUBLAS_STATUS_SUCCESS) { ctx->blas = nullptr; return fail(ctx, AH_ERR_CUDA_BASE, "cublasCreate failed"); }
-    }
-    if (cublasSetStream(ctx->blas, ctx->stream) != CUBLAS_STATUS_SUCCESS) return fail(ctx, AH_ERR_CUDA_BASE, "cublasSetStream failed");
     int rc;
     if ((rc = ensure(ctx, ctx->dPtrA, nb * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dPtrB, nb * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dPtrC, nb * 8))) return rc;
-    AH_CUDA(cudaMemcpyAsync(ctx->dPtrA.p, A_ptrs, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
-    AH_CUDA(cudaMemcpyAsync(ctx->dPtrB.p, B_ptrs, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
-    AH_CUDA(cudaMemcpyAsync(ctx->dPtrC.p, C_ptrs, nb * 8, cudaMemcpyHostToDevice, ctx->stream));
-    const double one = 1.0, zero = 0.0;
-    cublasStatus_t cs;
-    if (nb == 1) {
-        cs = cublasDgemm(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, (int)n, (int)k, &one, (const double *)A_ptrs[0], (int)lda,
-                         (const double *)B_ptrs[0], (int)ldb, &zero, (double *)C_ptrs[0], (int)ldc);
-    } else {
-        cs = cublasDgemmBatched(ctx->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)m, (int)n, (int)k, &one, (const double *const *)ctx->dPtrA.p, (int)lda,
-                                (const double *const *)ctx->dPtrB.p, (int)ldb, &zero, (double *const *)ctx->dPtrC.p, (int)ldc, (int)nb);
-    }
-    if (cs != CUBLAS_STATUS_SUCCESS) return fail(ctx, AH_ERR_CUDA_BASE, "cublasDgemm(Batched) failed with status " + std::to_string((int)cs));
-    AH_CUDA(cudaStreamSynchronize(ctx->stream));
-    return AH_OK;
+    if ((rc = h2d_staged(ctx, ctx->dPtrA.p, A_ptrs, nb * 8))) return rc;
+    if ((rc = h2d_staged(ctx, ctx->dPtrB.p, B_ptrs, nb * 8))) return rc;
+    if ((rc = h2d_staged(ctx, ctx->dPtrC.p, C_ptrs, nb * 8))) return rc;
+    AH_CUDA(cudaEventRecord(ctx->ev[8], ctx->stream));
+    rc = ah::launch_dgemm((const uint64_t *)ctx->dPtrA.p, (const uint64_t *)ctx->dPtrB.p, (const uint64_t *)ctx->dPtrC.p, (int)nb, (int)m, (int)n,
+                          (int)k, lda, ldb, ldc, ctx->sm_count, ctx->stream);
+    if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_dgemm_dmma launch");
+    AH_CUDA(cudaEventRecord(ctx->ev[9], ctx->stream));
+    return util_done(ctx);
 }
 
 int ah_scale_rows_phase(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src,
@@ -1134,15 +1153,59 @@ int ah_scale_rows_phase(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const doub
     AH_CUDA(cudaSetDevice(ctx->device));
     int rc;
     if ((rc = ensure(ctx, ctx->dScale, (size_t)nrows * ncomp * 8))) return rc;
-    AH_CUDA(cudaMemcpyAsync(ctx->dScale.p, phase, (size_t)nrows * ncomp * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = h2d_staged(ctx, ctx->dScale.p, phase, (size_t)nrows * ncomp * 8))) return rc;
     const int grid = ctx->sm_count * 8;
     if (ncomp == 2) k_scale_rows_phase<2><<<grid, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const double *)ctx->dScale.p, nrows, ncols);
     else k_scale_rows_phase<4><<<grid, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const double *)ctx->dScale.p, nrows, ncols);
     AH_CUDA(cudaGetLastError());
-    AH_CUDA(cudaStreamSynchronize(ctx->stream));
-    return AH_OK;
+    return util_done(ctx);
 }
 
+int ah_set_async(ah_ctx *ctx, int on) {
+    if (!ctx) return AH_ERR_INVALID_ARG;
+    ctx->async_utils = on != 0;
+    return AH_OK;
+}
+int ah_wait(ah_ctx *ctx) {
+    if (!ctx) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->hArenaUsed = 0;
+    AH_CUDA(cudaGetLastError());
+    return AH_OK;
+}
+int ah_last_gemm_ms(ah_ctx *ctx, double *ms) {
+    if (!ctx || !ms) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaEventSynchronize(ctx->ev[9]));
+    float t = 0.f;
+    AH_CUDA(cudaEventElapsedTime(&t, ctx->ev[8], ctx->ev[9]));
+    *ms = t;
+    return AH_OK;
+}
+int ah_measure_dmma_peak(ah_ctx *ctx, double *gfma_per_s, double *elapsed_ms) {
+    if (!ctx || !gfma_per_s) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    const int threads = 256, blocks = ctx->sm_count * 2, iters = 1 << 12;
+    int rc;
+    if ((rc = ensure(ctx, ctx->dStage[0], (size_t)threads * blocks * 8))) return rc;
+    double *o = (double *)ctx->dStage[0].p;
+    ah::k_dmma_burst<<<blocks, threads, 0, ctx->stream>>>(o, 16, 0.999999, 1e-7);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        AH_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+        ah::k_dmma_burst<<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.999999, 1e-7);
+        AH_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        AH_CUDA(cudaEventSynchronize(ctx->ev[1]));
+        float ms = 0.f;
+        AH_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        best = std::min(best, ms);
+    }
+    AH_CUDA(cudaGetLastError());
+    // one DMMA.8x8x4 = 8*8*4 = 256 FMA per warp
+    *gfma_per_s = (double)(threads / 32) * blocks * (double)iters * 16.0 * 256.0 / (best * 1e-3) / 1e9;
+    if (elapsed_ms) *elapsed_ms = best;
+    return AH_OK;
+}
 int ah_measure_fp64_peak(ah_ctx *ctx, double *ginstr_per_s, double *elapsed_ms) {
     if (!ctx || !ginstr_per_s) return AH_ERR_INVALID_ARG;
     AH_CUDA(cudaSetDevice(ctx->device));

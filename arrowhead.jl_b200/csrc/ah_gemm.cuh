@@ -1,0 +1,173 @@
+// ah_gemm.cuh -- the FP64 back-transform of tdc() as a hand-written sm_100a kernel.
+//
+//   E.vectors[1:k,:]   = E1.vectors * E.vectors[1:k,:]         (arrowhead7.jl:32)
+//   E.vectors[k+2:n,:] = E2.vectors * E.vectors[k+2:n,:]       (arrowhead7.jl:33)
+//
+// i.e. for every merge of one tree height C_b (m x n) = A_b (m x k) * B_b (k x n), column-major, addresses in
+// pointer arrays (all merges of a height have the same shape).  This is the one real contraction of the package;
+// FP64 has no tcgen05/TMEM path, the tensor-core instruction for binary64 on sm_100a is DMMA.8x8x4
+// (`mma.sync.aligned.m8n8k4.row.col.f64`), which is what this kernel issues.
+//
+// Tiling: one CTA = TM x TN tile of C, K in slices of 16 through a 3-stage cp.async ring in shared memory;
+// 8 warps as 2 x 4, each warp a (TM/2) x (TN/4) block of 8x8 DMMA tiles with the accumulators in registers.
+// Shared-memory layouts are padded so that every fragment load (one double per lane) is conflict-free:
+//   A tile  [kk][row]  column stride TM+4 doubles: the 4 k-columns of a fragment fall 8 banks apart
+//   B tile  [col][kk]  column stride 20 doubles  : the 4 columns of a half-warp fall 8 banks apart
+// Global loads are 8-byte cp.async (sub-blocks of the resident eigenvector matrices start at odd element offsets,
+// so 16-byte alignment cannot be assumed); rows/columns/k beyond the matrix edge are zero-filled by cp.async's
+// src-size operand, the epilogue is predicated.  Rounding: each C entry is a chain of fused multiply-adds over k in
+// ascending order (DMMA accumulates 4 products per instruction in order) -- one rounding per product-sum, as cuBLAS.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ah {
+
+constexpr int GK = 16;        // k-slice
+constexpr int GSTAGES = 3;
+constexpr int GT = 256;       // threads
+
+template <int TM, int TN>
+struct GemmSmem {
+    static constexpr int LDA = TM + 4;     // doubles per k-column of the A tile
+    static constexpr int LDB = GK + 4;     // doubles per column of the B tile
+    double A[GSTAGES][GK * LDA];
+    double B[GSTAGES][TN * LDB];
+};
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool valid) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 8 : 0;       // src-size 0: the 8 destination bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// grid: (ceil(n/TN), ceil(m/TM), nb)
+template <int TM, int TN>
+__global__ void __launch_bounds__(GT) k_dgemm_dmma(const uint64_t *__restrict__ Aptrs, const uint64_t *__restrict__ Bptrs,
+                                                   const uint64_t *__restrict__ Cptrs, int m, int n, int k, int64_t lda, int64_t ldb,
+                                                   int64_t ldc) {
+    extern __shared__ __align__(16) unsigned char gsm_raw[];
+    using S = GemmSmem<TM, TN>;
+    S &sm = *reinterpret_cast<S *>(gsm_raw);
+    constexpr int WM = TM / 2, WN = TN / 4;          // warp tile
+    constexpr int MT = WM / 8, NT = WN / 8;          // 8x8 DMMA tiles per warp
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 1) * WM, wn = (warp >> 1) * WN;
+    const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
+    const double *__restrict__ A = reinterpret_cast<const double *>(Aptrs[blockIdx.z]);
+    const double *__restrict__ B = reinterpret_cast<const double *>(Bptrs[blockIdx.z]);
+    double *__restrict__ C = reinterpret_cast<double *>(Cptrs[blockIdx.z]);
+
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    const int nslices = (k + GK - 1) / GK;
+    auto load_slice = [&](int s, int stage) {
+        const int k0 = s * GK;
+        // A tile: GK columns of TM rows; consecutive threads take consecutive rows (coalesced 8-byte loads)
+#pragma unroll
+        for (int it = 0; it < (GK * TM) / GT; ++it) {
+            const int e = it * GT + tid, kk = e / TM, r = e - kk * TM;
+            const bool ok = (row0 + r < m) && (k0 + kk < k);
+            cp_async8(&sm.A[stage][kk * S::LDA + r], ok ? A + (int64_t)(k0 + kk) * lda + row0 + r : A, ok);
+        }
+        // B tile: TN columns of GK rows; consecutive threads take consecutive k of one column
+#pragma unroll
+        for (int it = 0; it < (GK * TN) / GT; ++it) {
+            const int e = it * GT + tid, c = e / GK, kk = e - c * GK;
+            const bool ok = (col0 + c < n) && (k0 + kk < k);
+            cp_async8(&sm.B[stage][c * S::LDB + kk], ok ? B + (int64_t)(col0 + c) * ldb + k0 + kk : B, ok);
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < GSTAGES - 1; ++s) {
+        if (s < nslices) load_slice(s, s);
+        cp_async_commit();
+    }
+    const int ar = lane >> 2, ak = lane & 3;         // fragment coordinates: A[row ar][k ak], B[k ak][col ar]
+    for (int s = 0; s < nslices; ++s) {
+        cp_async_wait<GSTAGES - 2>();
+        __syncthreads();                             // slice s has landed for everyone; stage (s-1)%3 is free again
+        if (s + GSTAGES - 1 < nslices) load_slice(s + GSTAGES - 1, (s + GSTAGES - 1) % GSTAGES);
+        cp_async_commit();
+        const double *As = sm.A[s % GSTAGES], *Bs = sm.B[s % GSTAGES];
+#pragma unroll
+        for (int k4 = 0; k4 < GK; k4 += 4) {
+            double af[MT], bf[NT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) af[i] = As[(k4 + ak) * S::LDA + wm + i * 8 + ar];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) bf[j] = Bs[(wn + j * 8 + ar) * S::LDB + k4 + ak];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+    // epilogue: C fragment of a DMMA tile: row ar, columns 2*ak and 2*ak+1
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int r = row0 + wm + i * 8 + ar;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int c = col0 + wn + j * 8 + 2 * ak;
+            if (r < m) {
+                if (c < n) C[(int64_t)c * ldc + r] = acc[i][j][0];
+                if (c + 1 < n) C[(int64_t)(c + 1) * ldc + r] = acc[i][j][1];
+            }
+        }
+    }
+}
+
+template <int TM, int TN>
+inline int launch_dgemm_tile(const uint64_t *A, const uint64_t *B, const uint64_t *C, int nb, int m, int n, int k, int64_t lda,
+                             int64_t ldb, int64_t ldc, cudaStream_t st) {
+    const int smem = (int)sizeof(GemmSmem<TM, TN>);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_dgemm_dmma<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    dim3 grid((n + TN - 1) / TN, (m + TM - 1) / TM, nb);
+    k_dgemm_dmma<TM, TN><<<grid, GT, smem, st>>>(A, B, C, m, n, k, lda, ldb, ldc);
+    return (int)cudaGetLastError();
+}
+
+// tile choice: 128 x 128 where the problem fills the machine with it, 64 x 64 for the many small merges of the low levels
+inline int launch_dgemm(const uint64_t *A, const uint64_t *B, const uint64_t *C, int nb, int m, int n, int k, int64_t lda,
+                        int64_t ldb, int64_t ldc, int sm_count, cudaStream_t st) {
+    const int64_t big = (int64_t)((n + 127) / 128) * ((m + 127) / 128) * nb;
+    if (m >= 96 && n >= 96 && big >= sm_count) return launch_dgemm_tile<128, 128>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);
+    return launch_dgemm_tile<64, 64>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);
+}
+
+// DMMA.8x8x4 burst: independent accumulator chains from registers -> tensor-FP64 FMA rate (the GEMM's denominator)
+__global__ void __launch_bounds__(256) k_dmma_burst(double *out, int iters, double a0, double b0) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c[i][0] = threadIdx.x * 1e-9 + i; c[i][1] = 1.0 - i * 1e-3; }
+    double a = a0 + threadIdx.x * 1e-12, b = b0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += c[i][0] + c[i][1];
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
+}  // namespace ah

@@ -236,8 +236,9 @@ int ah_gather_permuted_batched(ah_ctx *ctx, int64_t nb, double *dst_dev, int64_t
 int ah_copy2d_batched(ah_ctx *ctx, int64_t nb, int64_t nrows, int64_t ncols, const uint64_t *dst_ptrs, int64_t ld_dst,
                       const uint64_t *src_ptrs, int64_t ld_src);
 /* C_b = A_b * B_b (m x k times k x n), all device, column-major, addresses in host arrays: the back-transform
- * `E.vectors[1:k,:] = E1.vectors*E.vectors[1:k,:]` (arrowhead7.jl:32-33) of a whole level in one cuBLAS
- * cublasDgemmBatched call (a plain library GEMM; the one tensor-core-eligible operation of the package). */
+ * `E.vectors[1:k,:] = E1.vectors*E.vectors[1:k,:]` (arrowhead7.jl:32-33) of a whole tree height in one launch of the
+ * library's own FP64 tensor-core kernel (csrc/ah_gemm.cuh: DMMA.8x8x4 = mma.sync.m8n8k4.f64, cp.async ring, 128x128 or
+ * 64x64 CTA tiles).  No cuBLAS anywhere in the library.  nb <= 65535. */
 int ah_dgemm_batched(ah_ctx *ctx, int64_t nb, int64_t m, int64_t n, int64_t k, const uint64_t *A_ptrs, int64_t lda,
                      const uint64_t *B_ptrs, int64_t ldb, const uint64_t *C_ptrs, int64_t ldc);
 
@@ -248,7 +249,20 @@ int ah_dgemm_batched(ah_ctx *ctx, int64_t nb, int64_t m, int64_t n, int64_t k, c
 int ah_scale_rows_phase(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src,
                         const double *phase, int ncomp, int64_t nrows, int64_t ncols);
 
+/* The device utilities above (set_identity, apply_givens_rows, gather_permuted[_batched], copy2d_batched,
+ * dgemm_batched, scale_rows_phase) synchronise the stream before they return.  ah_set_async(ctx, 1) turns them into
+ * enqueue-only calls (their host index / pointer arrays are staged through pinned memory, so they may be freed on
+ * return); ah_wait synchronises and reports any deferred CUDA error.  tdc() uses this to keep a whole tree height on
+ * the stream.  Calls that return data to the host (the solves, ah_gather_elements, ah_memcpy_d2h) always synchronise. */
+int ah_set_async(ah_ctx *ctx, int on);
+int ah_wait(ah_ctx *ctx);
+/* device time of the last ah_dgemm_batched launch (CUDA events around the kernel) */
+int ah_last_gemm_ms(ah_ctx *ctx, double *ms);
+
 /* ---- measurement helpers (used by bench.py for the roofline denominators) ---------------------- */
+/* DMMA.8x8x4 burst from registers on every SM: FP64 tensor-core rate in 1e9 FMA/s (x2 = GFLOP/s): the denominator of
+ * the back-transform GEMM's roofline. */
+int ah_measure_dmma_peak(ah_ctx *ctx, double *gfma_per_s, double *elapsed_ms);
 /* Dependent-free DFMA burst on every SM: returns FP64-pipe instruction issue rate in
  * 1e9 warp-lane-instructions/s (x2 = GFLOP/s) and the elapsed ms. */
 int ah_measure_fp64_peak(ah_ctx *ctx, double *ginstr_per_s, double *elapsed_ms);
