@@ -40,6 +40,7 @@ struct ah_ctx {
     int sm_count = 0;
     int quantum = -1;           // k_bisect time slice (steps): < 0 automatic, 0 off (tuning knob ARROWHEAD_B200_QUANTUM)
     int window = 2;             // time slicing starts when fewer than window x slots eigenpairs wait (ARROWHEAD_B200_WINDOW)
+    int spec = 1;               // speculative tail of k_bisect: idle slots evaluate the next midpoints (ARROWHEAD_B200_SPEC=0: off)
     unsigned bisect_tag = 0;    // per-launch tag of the requeue FIFO entries
     bool res_valid = false;     // dD / dZ still hold the inputs of the last solve (ah_resolve)
     int res_kind = 0;
@@ -414,7 +415,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                 ctx->bisect_tag = 1;
             }
             rc = ah::launch_bisect(L.kind, 0, P, Oc, ks, kb, cc, dlist, rlist, dcount, (unsigned long long *)ctx->dQueue.p,
-                                   (long long)(ctx->dQueue.cap / 8), ctx->bisect_tag, ctx->quantum, ctx->window, ctx->sm_count, st);
+                                   (long long)(ctx->dQueue.cap / 8), ctx->bisect_tag, ctx->quantum, ctx->window, ctx->spec, ctx->sm_count, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect launch");
             ctx->stats.launches += 2;   // k_prep, k_bisect round 0
             AH_CUDA(cudaEventRecord(E[2], st));
@@ -434,7 +435,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                 AH_CUDA(cudaEventRecord(SE[0], rs));
                 rc = ah::launch_rem3_prep(L.kind, P, Oc, ks, kb, guess, rlist, dlist, dcount, ctx->sm_count, rs);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_rem3_prep launch");
-                rc = ah::launch_bisect(L.kind, 1, P, Oc, ks, kb, guess, dlist, rlist, dcount, nullptr, 0, 0u, 0, 0, ctx->sm_count, rs);
+                rc = ah::launch_bisect(L.kind, 1, P, Oc, ks, kb, guess, dlist, rlist, dcount, nullptr, 0, 0u, 0, 0, 0, ctx->sm_count, rs);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect round 1 launch");
                 AH_CUDA(cudaEventRecord(SE[1], rs));
                 ctx->stats.launches += 2;
@@ -507,13 +508,16 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
 
 #ifdef AH_DIAG_TIMING
     {
-        unsigned long long tg[8];
+        unsigned long long tg[20];
         AH_CUDA(cudaMemcpyAsync(tg, (unsigned long long *)ctx->dCount.p + 152, sizeof tg, cudaMemcpyDeviceToHost, st));
         AH_CUDA(cudaStreamSynchronize(st));
         const double ctas = (double)std::max<unsigned long long>(1, tg[7]), sw = (double)std::max<unsigned long long>(1, tg[6]);
         fprintf(stderr, "[diag] k_bisect warp 0, cycles per sweep (mean over %llu CTAs, %.1f sweeps each): boundary %.0f | barrier2 wait %.0f | "
                         "param copy %.0f | tiles %.0f | reduce %.0f | barrier1 wait %.0f\n", tg[7], sw / ctas, tg[0] / sw, tg[1] / sw, tg[2] / sw,
                 tg[3] / sw, tg[4] / sw, tg[5] / sw);
+        fprintf(stderr, "[diag] slot 0's boundary, cycles per sweep: decide %.0f | finalize %.0f (%.3f/sweep) | swap check %.0f (%.3f) | requeue %.0f (%.3f) | "
+                        "ticket %.0f (%.3f) | resolve/poll %.0f (%.3f) | load KState %.0f\n", tg[8] / sw, tg[9] / sw, tg[15] / sw, tg[10] / sw, tg[16] / sw,
+                tg[11] / sw, tg[17] / sw, tg[12] / sw, tg[18] / sw, tg[13] / sw, tg[19] / sw, tg[14] / sw);
     }
 #endif
     // ---- per-k outputs -> host
@@ -728,6 +732,7 @@ int ah_create(ah_ctx **pctx, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char *q = getenv("ARROWHEAD_B200_QUANTUM")) ctx->quantum = atoi(q);
     if (const char *q = getenv("ARROWHEAD_B200_WINDOW")) ctx->window = std::max(1, atoi(q));
+    if (const char *q = getenv("ARROWHEAD_B200_SPEC")) ctx->spec = atoi(q) != 0;
     if ((e = cudaSetDevice(device)) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaSetDevice"); }
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;

@@ -9,7 +9,8 @@
 // (`mma.sync.aligned.m8n8k4.row.col.f64`), which is what this kernel issues.
 //
 // Tiling: one CTA = TM x TN tile of C, K in slices of 16 through a 3-stage cp.async ring in shared memory;
-// 8 warps as 2 x 4, each warp a (TM/2) x (TN/4) block of 8x8 DMMA tiles with the accumulators in registers.
+// WGM x WGN warps, each a (TM/WGM) x (TN/WGN) block of 8x8 DMMA tiles with the accumulators in registers
+// (128 x 128 with 16 warps of 32 x 32; 64 x 64 with 8 warps of 32 x 16 for small merges).
 // Shared-memory layouts are padded so that every fragment load (one double per lane) is conflict-free:
 //   A tile  [kk][row]  column stride TM+4 doubles: the 4 k-columns of a fragment fall 8 banks apart
 //   B tile  [col][kk]  column stride 20 doubles  : the 4 columns of a half-warp fall 8 banks apart
@@ -25,7 +26,6 @@ namespace ah {
 
 constexpr int GK = 16;        // k-slice
 constexpr int GSTAGES = 3;
-constexpr int GT = 256;       // threads
 
 template <int TM, int TN>
 struct GemmSmem {
@@ -48,18 +48,23 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// grid: (ceil(n/TN), ceil(m/TM), nb)
-template <int TM, int TN>
-__global__ void __launch_bounds__(GT) k_dgemm_dmma(const uint64_t *__restrict__ Aptrs, const uint64_t *__restrict__ Bptrs,
-                                                   const uint64_t *__restrict__ Cptrs, int m, int n, int k, int64_t lda, int64_t ldb,
-                                                   int64_t ldc) {
+// grid: (ceil(n/TN), ceil(m/TM), nb); WGM x WGN warps, each a (TM/WGM) x (TN/WGN) block of C
+template <int TM, int TN, int WGM, int WGN>
+__global__ void __launch_bounds__(32 * WGM * WGN) k_dgemm_dmma(const uint64_t *__restrict__ Aptrs, const uint64_t *__restrict__ Bptrs,
+                                                                const uint64_t *__restrict__ Cptrs, int m, int n, int k, int64_t lda,
+                                                                int64_t ldb, int64_t ldc) {
     extern __shared__ __align__(16) unsigned char gsm_raw[];
     using S = GemmSmem<TM, TN>;
     S &sm = *reinterpret_cast<S *>(gsm_raw);
-    constexpr int WM = TM / 2, WN = TN / 4;          // warp tile
+    constexpr int NTHR = 32 * WGM * WGN;
+    constexpr int WM = TM / WGM, WN = TN / WGN;      // warp tile
     constexpr int MT = WM / 8, NT = WN / 8;          // 8x8 DMMA tiles per warp
+    constexpr int AL = (GK * TM) / NTHR, BL = (GK * TN) / NTHR;   // cp.async per thread and slice (A, B)
+    constexpr int AKS = NTHR / TM;                   // k-columns of the A tile covered by one pass of the CTA
+    constexpr int BCS = NTHR / GK;                   // columns of the B tile covered by one pass
+    static_assert(AL >= 1 && BL >= 1 && AL * NTHR == GK * TM && BL * NTHR == GK * TN, "tile / thread-count mismatch");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp & 1) * WM, wn = (warp >> 1) * WN;
+    const int wm = (warp % WGM) * WM, wn = (warp / WGM) * WN;
     const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
     const double *__restrict__ A = reinterpret_cast<const double *>(Aptrs[blockIdx.z]);
     const double *__restrict__ B = reinterpret_cast<const double *>(Bptrs[blockIdx.z]);
@@ -71,22 +76,38 @@ __global__ void __launch_bounds__(GT) k_dgemm_dmma(const uint64_t *__restrict__ 
 #pragma unroll
         for (int j = 0; j < NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
+    // ---- per-thread load plan, fixed for the whole K loop: the address arithmetic of a slice is one add per copy.
+    // A tile: thread -> row ra, k-columns ka0 + it*AKS.   B tile: thread -> k-row kb, columns cb0 + it*BCS.
+    const int ra = tid % TM, ka0 = tid / TM;
+    const int kb = tid % GK, cb0 = tid / GK;
+    const bool a_row_ok = row0 + ra < m;
+    const double *pa = A + (int64_t)ka0 * lda + (a_row_ok ? row0 + ra : 0);
+    const double *pb = B + (int64_t)(col0 + cb0) * ldb + kb;
+    unsigned b_col_ok = 0;
+#pragma unroll
+    for (int it = 0; it < BL; ++it) b_col_ok |= (col0 + cb0 + it * BCS < n ? 1u : 0u) << it;
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(&sm.A[0][ka0 * S::LDA + ra]);
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(&sm.B[0][cb0 * S::LDB + kb]);
+    constexpr uint32_t A_STAGE = GK * S::LDA * 8, B_STAGE = TN * S::LDB * 8;
+
     const int nslices = (k + GK - 1) / GK;
     auto load_slice = [&](int s, int stage) {
         const int k0 = s * GK;
-        // A tile: GK columns of TM rows; consecutive threads take consecutive rows (coalesced 8-byte loads)
+        const double *ga = pa + (int64_t)k0 * lda;
+        const double *gb = pb + k0;
 #pragma unroll
-        for (int it = 0; it < (GK * TM) / GT; ++it) {
-            const int e = it * GT + tid, kk = e / TM, r = e - kk * TM;
-            const bool ok = (row0 + r < m) && (k0 + kk < k);
-            cp_async8(&sm.A[stage][kk * S::LDA + r], ok ? A + (int64_t)(k0 + kk) * lda + row0 + r : A, ok);
+        for (int it = 0; it < AL; ++it) {
+            const bool ok = a_row_ok && (k0 + ka0 + it * AKS < k);
+            const int bytes = ok ? 8 : 0;                        // src-size 0: the destination is zero-filled
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa + stage * A_STAGE + it * AKS * S::LDA * 8),
+                         "l"(ok ? ga + (int64_t)it * AKS * lda : A), "r"(bytes) : "memory");
         }
-        // B tile: TN columns of GK rows; consecutive threads take consecutive k of one column
 #pragma unroll
-        for (int it = 0; it < (GK * TN) / GT; ++it) {
-            const int e = it * GT + tid, c = e / GK, kk = e - c * GK;
-            const bool ok = (col0 + c < n) && (k0 + kk < k);
-            cp_async8(&sm.B[stage][c * S::LDB + kk], ok ? B + (int64_t)(col0 + c) * ldb + k0 + kk : B, ok);
+        for (int it = 0; it < BL; ++it) {
+            const bool ok = ((b_col_ok >> it) & 1u) && (k0 + kb < k);
+            const int bytes = ok ? 8 : 0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sb + stage * B_STAGE + it * BCS * S::LDB * 8),
+                         "l"(ok ? gb + (int64_t)it * BCS * ldb : B), "r"(bytes) : "memory");
         }
     };
 
@@ -96,12 +117,13 @@ __global__ void __launch_bounds__(GT) k_dgemm_dmma(const uint64_t *__restrict__ 
         cp_async_commit();
     }
     const int ar = lane >> 2, ak = lane & 3;         // fragment coordinates: A[row ar][k ak], B[k ak][col ar]
+    int stage = 0, nstage = GSTAGES - 1;             // stage of slice s, stage that slice s + GSTAGES - 1 goes into
     for (int s = 0; s < nslices; ++s) {
         cp_async_wait<GSTAGES - 2>();
-        __syncthreads();                             // slice s has landed for everyone; stage (s-1)%3 is free again
-        if (s + GSTAGES - 1 < nslices) load_slice(s + GSTAGES - 1, (s + GSTAGES - 1) % GSTAGES);
+        __syncthreads();                             // slice s has landed for everyone; the stage of slice s-1 is free again
+        if (s + GSTAGES - 1 < nslices) load_slice(s + GSTAGES - 1, nstage);
         cp_async_commit();
-        const double *As = sm.A[s % GSTAGES], *Bs = sm.B[s % GSTAGES];
+        const double *As = sm.A[stage], *Bs = sm.B[stage];
 #pragma unroll
         for (int k4 = 0; k4 < GK; k4 += 4) {
             double af[MT], bf[NT];
@@ -114,6 +136,8 @@ __global__ void __launch_bounds__(GT) k_dgemm_dmma(const uint64_t *__restrict__ 
 #pragma unroll
                 for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
+        stage = (stage + 1 == GSTAGES) ? 0 : stage + 1;
+        nstage = (nstage + 1 == GSTAGES) ? 0 : nstage + 1;
     }
     cp_async_wait<0>();
     // epilogue: C fragment of a DMMA tile: row ar, columns 2*ak and 2*ak+1
@@ -131,27 +155,39 @@ __global__ void __launch_bounds__(GT) k_dgemm_dmma(const uint64_t *__restrict__ 
     }
 }
 
-template <int TM, int TN>
+template <int TM, int TN, int WGM, int WGN>
 inline int launch_dgemm_tile(const uint64_t *A, const uint64_t *B, const uint64_t *C, int nb, int m, int n, int k, int64_t lda,
                              int64_t ldb, int64_t ldc, cudaStream_t st) {
     const int smem = (int)sizeof(GemmSmem<TM, TN>);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_dgemm_dmma<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(k_dgemm_dmma<TM, TN, WGM, WGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     dim3 grid((n + TN - 1) / TN, (m + TM - 1) / TM, nb);
-    k_dgemm_dmma<TM, TN><<<grid, GT, smem, st>>>(A, B, C, m, n, k, lda, ldb, ldc);
+    k_dgemm_dmma<TM, TN, WGM, WGN><<<grid, 32 * WGM * WGN, smem, st>>>(A, B, C, m, n, k, lda, ldb, ldc);
     return (int)cudaGetLastError();
 }
 
-// tile choice: 128 x 128 where the problem fills the machine with it, 64 x 64 for the many small merges of the low levels
+#ifndef AH_GEMM_VARIANT
+#define AH_GEMM_VARIANT 0
+#endif
+// tile choice: 128 x 128 (16 warps of 32 x 32) where the problem fills the machine with it, 64 x 64 (8 warps of 32 x 16) for the
+// many small merges of the low tree levels
 inline int launch_dgemm(const uint64_t *A, const uint64_t *B, const uint64_t *C, int nb, int m, int n, int k, int64_t lda,
                         int64_t ldb, int64_t ldc, int sm_count, cudaStream_t st) {
     const int64_t big = (int64_t)((n + 127) / 128) * ((m + 127) / 128) * nb;
-    if (m >= 96 && n >= 96 && big >= sm_count) return launch_dgemm_tile<128, 128>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);
-    return launch_dgemm_tile<64, 64>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);
+    if (m >= 96 && n >= 96 && big >= sm_count) {
+#if AH_GEMM_VARIANT == 1
+        return launch_dgemm_tile<128, 128, 2, 4>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);     // 8 warps of 64 x 32
+#elif AH_GEMM_VARIANT == 2
+        return launch_dgemm_tile<128, 64, 2, 4>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);      // 8 warps of 64 x 16, two CTAs per SM
+#else
+        return launch_dgemm_tile<128, 128, 4, 4>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);
+#endif
+    }
+    return launch_dgemm_tile<64, 64, 2, 4>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);
 }
 
 // DMMA.8x8x4 burst: independent accumulator chains from registers -> tensor-FP64 FMA rate (the GEMM's denominator)

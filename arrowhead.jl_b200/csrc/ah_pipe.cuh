@@ -344,6 +344,10 @@ struct BisectShared {
     long long skip[BJ];            // 0-based index of the slot's shift pole, -1: none (idle slot, or Remedy-3 round)
     int act[BJ];                   // coming sweep: 1 slot is bisecting, 2 slot waits for its ticket, 0 slot has retired
     double save[BJ];               // accumulator of slot j saved by the one thread that owns its shift pole
+    // speculative tail (see k_bisect): helpers of leader slot j for the coming sweep and the bisection points they evaluate
+    int grpn[BJ];                  // number of helper slots of slot j: 0, 2 (both next midpoints) or 6 (the next two levels)
+    int grp[BJ][6];
+    double grp_pt[BJ][6];
     BSlot slot[BJ];
 };
 
@@ -465,7 +469,7 @@ template <int KIND, int ROUND, int NSLOT>
 __global__ void __launch_bounds__(BT, BCTAS)
 k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *__restrict__ dlist,
          int64_t *__restrict__ rlist, unsigned long long *dcount, unsigned long long *__restrict__ queue, long long qcap,
-         unsigned tag, int quantum, int window) {
+         unsigned tag, int quantum, int window, int spec) {
     static_assert(NSLOT >= 1 && NSLOT <= BJ && NSLOT <= BW, "one warp per slot");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BisectShared &sh = *reinterpret_cast<BisectShared *>(smem_raw);
@@ -476,7 +480,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         for (int s = 0; s < BS; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], BW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < NSLOT) { sh.slot[tid].phase = PH_FREE; sh.skip[tid] = -1; sh.act[tid] = 0; sh.hot[tid] = make_double2(0.0, 0.0); }
+    if (tid < NSLOT) { sh.slot[tid].phase = PH_FREE; sh.skip[tid] = -1; sh.act[tid] = 0; sh.hot[tid] = make_double2(0.0, 0.0); sh.grpn[tid] = 0; }
     if (ROUND == 1) { cnt = (int64_t)dcount[2]; quantum = 0; }   // round 1 works through the (short) Remedy-3 list
 #if AH_STAGGER
     // Every sweep is ntiles tiles for every CTA, so the two CTAs of an SM would reach their sweep boundaries (reduce,
@@ -525,9 +529,15 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
 #ifdef AH_DIAG_TIMING
     // diagnostic build only: where warp 0 spends its cycles (clock64 deltas summed per CTA, atomically added to dcount[152..159])
     long long tg_boundary = 0, tg_b2 = 0, tg_param = 0, tg_tiles = 0, tg_reduce = 0, tg_b1 = 0, tg_sweeps = 0, tg_mark = clock64();
+    long long tb_decide = 0, tb_final = 0, tb_swapchk = 0, tb_requeue = 0, tb_ticket = 0, tb_resolve = 0, tb_load = 0, tb_n_final = 0,
+              tb_n_swapchk = 0, tb_n_requeue = 0, tb_n_ticket = 0, tb_n_poll = 0, tb_mark = 0;
 #define AH_TG(var) do { if (tid == 0) { const long long now__ = clock64(); var += now__ - tg_mark; tg_mark = now__; } } while (0)
+#define AH_TB_START() do { if (tid == 0) tb_mark = clock64(); } while (0)
+#define AH_TB(var, cnt) do { if (tid == 0) { const long long now__ = clock64(); var += now__ - tb_mark; tb_mark = now__; cnt += 1; } } while (0)
 #else
 #define AH_TG(var) do { } while (0)
+#define AH_TB_START() do { } while (0)
+#define AH_TB(var, cnt) do { } while (0)
 #endif
     bool first = true;
     while (true) {
@@ -535,8 +545,12 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         // ================= sweep boundary: warp j advances slot j =================
         if (warp < NSLOT) {
             BSlot &S = sh.slot[warp];
-            if (!first && S.phase == PH_BISECT) {
-                double sum = (lane < BW) ? sh.part[warp][lane] : 0.0;
+            AH_TB_START();
+            // one bisection step of this slot from the partial sums that slot `ps` accumulated in the sweep just finished
+            // (ps == warp: the slot's own; otherwise a helper slot that evaluated the slot's NEXT point, see below);
+            // returns 1 / 0 for the two halves, -1 when the eigenpair left the slot (NaN sweep: hand-over to k_full)
+            auto bisection_step = [&](int ps) -> int {
+                double sum = (lane < BW) ? sh.part[ps][lane] : 0.0;
 #pragma unroll
                 for (int o = BW / 2; o > 0; o >>= 1) {
                     const double p = __shfl_xor_sync(0xffffffffu, sum, o);
@@ -557,7 +571,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                         S.phase = PH_FREE;
                     }
                     __syncwarp();
-                    goleft = false;
+                    return -1;
                 } else if (ROUND == 0) {
                     sum = __dmul_rn(sum, S.wz2);
                     if (KIND != KIND_DPR1) sum = __dadd_rn(sum, __ddiv_rn(S.wz2, __dadd_rn(0.0, -m)));
@@ -568,14 +582,38 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                     goleft = sign_jl(S.b) * F < 0.0;
                 }
                 __syncwarp();
-                if (lane == 0 && S.phase == PH_BISECT) {
+                if (lane == 0) {
                     if (goleft) S.left = m; else S.right = m;
                     S.m = (S.left + S.right) / 2.0;
                     S.steps += 1;
                     S.q += 1;
                 }
                 __syncwarp();
+                return goleft ? 1 : 0;
+            };
+            if (!first && S.phase == PH_BISECT) {
+                const int g1 = bisection_step(warp);
+                // Speculative tail: helper slots (idle slots of this CTA) evaluated F at the midpoints of both halves
+                // (and, with six helpers, of all four quarters) in the same sweep, so the step(s) that the reference
+                // would take next are decided here from their sums -- same points, same sums, same decisions, in the
+                // same order; a level is used only if the bracket has not converged and the helper's point is bitwise
+                // the slot's new midpoint.
+                const int nh = (ROUND == 0) ? sh.grpn[warp] : 0;
+                if (nh >= 2 && g1 >= 0 && !bisect_converged(S)) {
+                    const int h1 = g1 ? 1 : 0;                       // goleft: bracket [m, right] -> point B, else point A
+                    if (sh.grp_pt[warp][h1] == S.m) {
+                        const int g2 = bisection_step(sh.grp[warp][h1]);
+                        if (nh >= 6 && g2 >= 0 && !bisect_converged(S)) {
+                            const int h2 = 2 + 2 * h1 + (g2 ? 1 : 0);
+                            if (sh.grp_pt[warp][h2] == S.m) bisection_step(sh.grp[warp][h2]);
+                        }
+                    }
+                }
             }
+#ifdef AH_DIAG_TIMING
+            long long tb_dummy = 0;
+            AH_TB(tb_decide, tb_dummy);
+#endif
             while (true) {
                 if (S.phase == PH_BISECT) {
                     if (bisect_converged(S)) {   // (the reference tests before the first step, too) -> finalise
@@ -583,6 +621,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                         __syncwarp();
                         if (lane == 0) { if (quantum > 0) atomicAdd(dcount + 5, 1ull); S.phase = PH_FREE; }
                         __syncwarp();
+                        AH_TB(tb_final, tb_n_final);
                     } else {
                         // time slice used up and others are waiting -> back of the queue
                         int swap = 0;
@@ -603,6 +642,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                                 S.q = 0;
                             }
                             swap = __shfl_sync(0xffffffffu, swap, 0);
+                            AH_TB(tb_swapchk, tb_n_swapchk);
                         }
                         if (!swap) break;
                         if (lane == 0) {
@@ -615,6 +655,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                             S.phase = PH_FREE;
                         }
                         __syncwarp();
+                        AH_TB(tb_requeue, tb_n_requeue);
                     }
                 }
                 if (S.phase == PH_DONE) break;
@@ -627,6 +668,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                 if (S.phase == PH_FREE) {
                     if (lane == 0) { S.ticket = atomicAdd(tickets, 1ull); S.phase = PH_PENDING; }
                     __syncwarp();
+                    AH_TB(tb_ticket, tb_n_ticket);
                 }
                 // PH_PENDING: which eigenpair does the ticket stand for?
                 long long col = -1;      // >= 0: column of the block, -1: not there yet, -2: never
@@ -642,6 +684,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                     }
                 }
                 col = __shfl_sync(0xffffffffu, col, 0);
+                AH_TB(tb_resolve, tb_n_poll);
                 if (col < 0) {
                     __syncwarp();
                     if (lane == 0 && col == -2) S.phase = PH_DONE;
@@ -668,6 +711,9 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                     S.phase = PH_BISECT;
                 }
                 __syncwarp();
+#ifdef AH_DIAG_TIMING
+                AH_TB(tb_load, tb_dummy);
+#endif
             }
             if (lane == 0) {
                 const bool act = S.phase == PH_BISECT;
@@ -680,6 +726,54 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         AH_TG(tg_boundary);
         __syncthreads();
         AH_TG(tg_b2);
+
+        // ================= speculative tail: idle slots help the slots that still bisect =================
+        // Towards the end of a launch a CTA holds fewer eigenpairs than slots, and a bisection is a chain of ~55
+        // DEPENDENT sweeps: the last eigenpairs (up to 73 steps) would run on alone while every sweep still evaluates all
+        // NSLOT slots.  An idle slot therefore evaluates, for a slot that still bisects, the point that slot will need
+        // NEXT: with two helpers both possible next midpoints (two bisection steps per sweep), with six the two next
+        // levels (three steps per sweep).  The arithmetic of every F(m) is unchanged, so results stay bit-identical.
+        if (ROUND == 0 && spec) {
+            unsigned busy = 0, idle = 0;
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j) { if (sh.act[j] == 1) busy |= 1u << j; else idle |= 1u << j; }
+            const int nb = __popc(busy), ni = __popc(idle);
+            const int h = (nb == 0) ? 0 : (ni >= 6 * nb ? 6 : (ni >= 2 * nb ? 2 : 0));
+            if (h) {                                                    // CTA-uniform
+                if (warp < NSLOT && lane == 0) {
+                    auto nth_bit = [](unsigned mask, int r) { for (int q = 0; q < r; ++q) mask &= mask - 1; return __ffs(mask) - 1; };
+                    if ((busy >> warp) & 1u) {                          // leader: its helpers, in ascending slot order
+                        const int rank = __popc(busy & ((1u << warp) - 1u));
+                        for (int t = 0; t < h; ++t) sh.grp[warp][t] = nth_bit(idle, rank * h + t);
+                        sh.grpn[warp] = h;
+                    } else {
+                        const int ri = __popc(idle & ((1u << warp) - 1u));
+                        if (ri < nb * h) {                              // helper number t of leader L
+                            const int L = nth_bit(busy, ri / h), t = ri % h;
+                            const BSlot &Ls = sh.slot[L];
+                            const double l = Ls.left, r = Ls.right, m = Ls.m;
+                            const double mA = (l + m) / 2.0, mB = (m + r) / 2.0;
+                            double pt;
+                            switch (t) {
+                                case 0: pt = mA; break;
+                                case 1: pt = mB; break;
+                                case 2: pt = (l + mA) / 2.0; break;
+                                case 3: pt = (mA + m) / 2.0; break;
+                                case 4: pt = (m + mB) / 2.0; break;
+                                default: pt = (mB + r) / 2.0; break;
+                            }
+                            sh.grp_pt[L][t] = pt;
+                            sh.hot[warp] = make_double2(Ls.sigma, pt);
+                            sh.skip[warp] = (long long)(Ls.i - 1);
+                        }
+                        sh.grpn[warp] = 0;
+                    }
+                }
+                __syncthreads();
+            } else if (warp < NSLOT && lane == 0) {
+                sh.grpn[warp] = 0;
+            }
+        }
 
         // ================= per-thread copies of the sweep parameters =================
         unsigned actmask = 0;
@@ -789,6 +883,9 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         atomicAdd(dcount + 154, (unsigned long long)tg_param); atomicAdd(dcount + 155, (unsigned long long)tg_tiles);
         atomicAdd(dcount + 156, (unsigned long long)tg_reduce); atomicAdd(dcount + 157, (unsigned long long)tg_b1);
         atomicAdd(dcount + 158, (unsigned long long)tg_sweeps); atomicAdd(dcount + 159, 1ull);
+        const long long tb[12] = {tb_decide, tb_final, tb_swapchk, tb_requeue, tb_ticket, tb_resolve, tb_load, tb_n_final, tb_n_swapchk, tb_n_requeue,
+                                  tb_n_ticket, tb_n_poll};
+        for (int q = 0; q < 12; ++q) atomicAdd(dcount + 160 + q, (unsigned long long)tb[q]);
     }
 #endif
 
@@ -807,8 +904,14 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
 constexpr int RT = 256;
 static_assert(RT == BT, "the direct bisection reproduces k_bisect's summation order thread by thread");
 
+#ifndef AH_REM3_RU
+#define AH_REM3_RU 4
+#endif
+#ifndef AH_REM3_MINB
+#define AH_REM3_MINB 1
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(RT)
+__global__ void __launch_bounds__(RT, AH_REM3_MINB)
 k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t *__restrict__ rlist, int64_t *__restrict__ dlist,
             unsigned long long *dcount) {
     __shared__ double red[2 * (RT / 32) + 2];
@@ -878,7 +981,7 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
                 // One CTA per eigenpair: a sweep is latency-bound on the L2 loads unless several tiles are in flight.  The
                 // loads of RU tiles are issued together and the next group is fetched while this one is evaluated; the
                 // terms are still accumulated tile by tile, pair by pair -- k_bisect's order, bit for bit.
-                constexpr int RU = 4, RH = BE / 2;
+                constexpr int RU = AH_REM3_RU, RH = BE / 2;
                 double acc = 0.0;
                 double2 dcur[RU][RH], wcur[RU][RH], dnxt[RU][RH], wnxt[RU][RH];
                 auto fetch = [&](int tile0, double2 (&dd)[RU][RH], double2 (&ww)[RU][RH]) {
@@ -1150,7 +1253,7 @@ inline size_t bisect_queue_entries(int64_t cnt) { return (size_t)cnt * 24 + 8192
 // window: time slicing starts when fewer than window x (all slots) eigenpairs are waiting; tag: unique per launch, != 0
 inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O, KState *ks, int64_t kbase, int64_t cnt,
                          int64_t *dlist, int64_t *rlist, unsigned long long *dcount, unsigned long long *queue, long long qcap,
-                         unsigned tag, int quantum, int window, int sm_count, cudaStream_t st) {
+                         unsigned tag, int quantum, int window, int spec, int sm_count, cudaStream_t st) {
     const int smem = (int)sizeof(BisectShared);
     const int64_t cap = (int64_t)sm_count * BCTAS;
     // Round 0: 8 slots per CTA unless the block has fewer than 8 (7) eigenpairs per CTA of a full grid -- then 7 (6)
@@ -1168,7 +1271,7 @@ inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O
         // and nothing ever waits when every eigenpair has a slot of its own from the start
         quantum = (cnt <= (int64_t)grid * nslot) ? 0 : (int)std::min<int64_t>(32, std::max<int64_t>(8, 128 / std::max<int64_t>(1, ntiles)));
     }
-#define AH_LAUNCH_BISECT(KD, RD, NS) k_bisect<KD, RD, NS><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount, queue, qcap, tag, quantum, window)
+#define AH_LAUNCH_BISECT(KD, RD, NS) k_bisect<KD, RD, NS><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount, queue, qcap, tag, quantum, window, spec)
 #define AH_LAUNCH_KIND(RD, NS)                                          \
     switch (kind) {                                                     \
         case KIND_ARROW: AH_LAUNCH_BISECT(KIND_ARROW, RD, NS); break;   \

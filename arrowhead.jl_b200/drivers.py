@@ -463,9 +463,11 @@ def tdc_device(dv, ev, *, ctx: Context | None = None, vectors="host", rotation="
     height at a time: all merges of one height are independent, so their arrow problems are solved in ONE batched
     launch (ah_symarrow_eigen_batched; large ones through the fast pipeline), their merge vectors z (:28) are read
     from the resident eigenvector blocks, the final `view(U,rows,es)` of the arrow driver is one batched gather, and
-    the back-transforms `E1.vectors*E.vectors[1:k,:]`, `E2.vectors*E.vectors[k+2:n,:]` (:32-33) are two
-    cublasDgemmBatched calls per size class.  Host work is the reference's host logic only: stable sorts, the
-    (exact) deflation tests, index bookkeeping.  Node [lo,hi) keeps its eigenvectors in the diagonal block
+    the back-transforms `E1.vectors*E.vectors[1:k,:]`, `E2.vectors*E.vectors[k+2:n,:]` (:32-33) are two launches
+    per size class of the library's own FP64 tensor-core GEMM (ah_dgemm_batched: DMMA.8x8x4, csrc/ah_gemm.cuh).
+    The gathers, copies and GEMMs of a height are enqueued without host synchronisation (ah_set_async); the host
+    only waits where it needs data back (eigenvalues of the merges, the merge vectors z).  Host work is the
+    reference's host logic only: stable sorts, the (exact) deflation tests, index bookkeeping.  Node [lo,hi) keeps its eigenvectors in the diagonal block
     [lo:hi, lo:hi] of one of three n x n buffers (height mod 3), so children are never overwritten while read.
     Merges that need deflation take the general per-problem driver (eigen_symarrow)."""
     ctx = ctx or get_context()
@@ -503,9 +505,19 @@ def tdc_device(dv, ev, *, ctx: Context | None = None, vectors="host", rotation="
 
         def free(self):
             pass
+    ctx.set_async(True)
+    try:
+        return _tdc_levels(ctx, dv, ev, n, by_height, height, Q, qbase, s_base, wp_base, _View, vectors, rotation)
+    finally:
+        ctx.set_async(False)
+        ctx.wait()
+
+
+def _tdc_levels(ctx, dv, ev, n, by_height, height, Q, qbase, s_base, wp_base, _View, vectors, rotation):
     ctx.set_identity(Q.ptr, n, n, n)                                  # leaves: U = [1] in buffer 0
     lam = {(i, i + 1): dv[i:i + 1] for i in range(n)}                 # eigenvalues of every finished node
-    stats = {"levels": 0, "batched_problems": 0, "pipeline_problems": 0, "driver_problems": 0, "gemm_calls": 0}
+    stats = {"levels": 0, "batched_problems": 0, "pipeline_problems": 0, "driver_problems": 0, "gemm_calls": 0, "gemm_flops": 0.0,
+             "gemm_shapes": []}
     for h in sorted(by_height):
         stats["levels"] += 1
         groups: dict[int, list] = {}
@@ -584,10 +596,14 @@ def tdc_device(dv, ev, *, ctx: Context | None = None, vectors="host", rotation="
             ctx.dgemm_batched(k, m, k, ql, n, wp, m, qout, n)
             ctx.copy2d_batched(1, m, qout + np.uint64(8 * k), n, wp + np.uint64(8 * k), m)
             stats["gemm_calls"] += 1
+            stats["gemm_flops"] += 2.0 * nb * k * m * k
+            stats["gemm_shapes"].append((nb, k, m, k))
             if r:
                 qr = np.uint64(qbase(tr)) + 8 * ((p + 1) * n + (p + 1)).astype(np.uint64)
                 ctx.dgemm_batched(r, m, r, qr, n, wp + np.uint64(8 * (k + 1)), m, qout + np.uint64(8 * (k + 1)), n)
                 stats["gemm_calls"] += 1
+                stats["gemm_flops"] += 2.0 * nb * r * m * r
+                stats["gemm_shapes"].append((nb, r, m, r))
             Wp.free()
             for b, node in enumerate(nodes):
                 lam[node] = L[b]

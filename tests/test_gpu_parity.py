@@ -527,8 +527,10 @@ def test_time_slicing_is_bitwise_schedule_independent(kind, monkeypatch):
     import torch
     n = 7000                                  # ~3 eigenpairs per slot on a B200: there is always something waiting
     outs = []
-    for quantum, window in (("0", "2"), (None, None), ("1", "100000"), ("5", "3")):
-        for name, val in (("ARROWHEAD_B200_QUANTUM", quantum), ("ARROWHEAD_B200_WINDOW", window)):
+    # (quantum, window, speculative tail): no slicing, the defaults, a pathological schedule, and the same without the
+    # helper slots that evaluate the next midpoints at the end of a launch
+    for quantum, window, spec in (("0", "2", "0"), (None, None, None), ("1", "100000", None), ("5", "3", "0"), (None, None, "0"), ("0", "2", None)):
+        for name, val in (("ARROWHEAD_B200_QUANTUM", quantum), ("ARROWHEAD_B200_WINDOW", window), ("ARROWHEAD_B200_SPEC", spec)):
             if val is None:
                 monkeypatch.delenv(name, raising=False)
             else:
