@@ -1137,15 +1137,16 @@ int ah_dgemm_batched(ah_ctx *ctx, int64_t nb, int64_t m, int64_t n, int64_t k, c
     if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX || nb > 65535) return fail(ctx, AH_ERR_INVALID_ARG, "ah_dgemm_batched: dimension too large");
     AH_CUDA(cudaSetDevice(ctx->device));
     int rc;
-    if ((rc = ensure(ctx, ctx->dPtrA, nb * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->dPtrB, nb * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->dPtrC, nb * 8))) return rc;
-    if ((rc = h2d_staged(ctx, ctx->dPtrA.p, A_ptrs, nb * 8))) return rc;
-    if ((rc = h2d_staged(ctx, ctx->dPtrB.p, B_ptrs, nb * 8))) return rc;
-    if ((rc = h2d_staged(ctx, ctx->dPtrC.p, C_ptrs, nb * 8))) return rc;
+    // the three pointer arrays travel in one staged copy
+    if ((rc = ensure(ctx, ctx->dPtrA, 3 * nb * 8))) return rc;
+    std::vector<uint64_t> ptrs((size_t)(3 * nb));
+    std::memcpy(ptrs.data(), A_ptrs, nb * 8);
+    std::memcpy(ptrs.data() + nb, B_ptrs, nb * 8);
+    std::memcpy(ptrs.data() + 2 * nb, C_ptrs, nb * 8);
+    if ((rc = h2d_staged(ctx, ctx->dPtrA.p, ptrs.data(), 3 * nb * 8))) return rc;
+    const uint64_t *dp = (const uint64_t *)ctx->dPtrA.p;
     AH_CUDA(cudaEventRecord(ctx->ev[8], ctx->stream));
-    rc = ah::launch_dgemm((const uint64_t *)ctx->dPtrA.p, (const uint64_t *)ctx->dPtrB.p, (const uint64_t *)ctx->dPtrC.p, (int)nb, (int)m, (int)n,
-                          (int)k, lda, ldb, ldc, ctx->sm_count, ctx->stream);
+    rc = ah::launch_dgemm(dp, dp + nb, dp + 2 * nb, (int)nb, (int)m, (int)n, (int)k, lda, ldb, ldc, ctx->sm_count, ctx->stream);
     if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_dgemm_dmma launch");
     AH_CUDA(cudaEventRecord(ctx->ev[9], ctx->stream));
     return util_done(ctx);

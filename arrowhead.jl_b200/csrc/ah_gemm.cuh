@@ -10,7 +10,7 @@
 //
 // Tiling: one CTA = TM x TN tile of C, K in slices of 16 through a 3-stage cp.async ring in shared memory;
 // WGM x WGN warps, each a (TM/WGM) x (TN/WGN) block of 8x8 DMMA tiles with the accumulators in registers
-// (128 x 128 with 16 warps of 32 x 32; 64 x 64 with 8 warps of 32 x 16 for small merges).
+// (128 x 64 with 8 warps of 64 x 16, two CTAs per SM; 64 x 64 with 8 warps of 32 x 16 for small merges).
 // Shared-memory layouts are padded so that every fragment load (one double per lane) is conflict-free:
 //   A tile  [kk][row]  column stride TM+4 doubles: the 4 k-columns of a fragment fall 8 banks apart
 //   B tile  [col][kk]  column stride 20 doubles  : the 4 columns of a half-warp fall 8 banks apart
@@ -24,8 +24,14 @@
 
 namespace ah {
 
-constexpr int GK = 16;        // k-slice
-constexpr int GSTAGES = 3;
+#ifndef AH_GEMM_GK
+#define AH_GEMM_GK 16
+#endif
+#ifndef AH_GEMM_STAGES
+#define AH_GEMM_STAGES 3
+#endif
+constexpr int GK = AH_GEMM_GK;            // k-slice held by one stage of the ring
+constexpr int GSTAGES = AH_GEMM_STAGES;
 
 template <int TM, int TN>
 struct GemmSmem {
@@ -171,20 +177,22 @@ inline int launch_dgemm_tile(const uint64_t *A, const uint64_t *B, const uint64_
 }
 
 #ifndef AH_GEMM_VARIANT
-#define AH_GEMM_VARIANT 0
+#define AH_GEMM_VARIANT 2
 #endif
-// tile choice: 128 x 128 (16 warps of 32 x 32) where the problem fills the machine with it, 64 x 64 (8 warps of 32 x 16) for the
-// many small merges of the low tree levels
+// Tile choice (measured on B200 on the back-transform shapes of tdc n = 8192, tools/gemm_bench.py): 128 x 64 tiles with
+// 8 warps of 64 x 16 and TWO CTAs per SM (one computes through the other's slice barrier) reach 30.4 TFLOP/s at
+// 4096 x 8192 x 4096; 128 x 128 tiles with one CTA per SM stay at 28 TFLOP/s whether 8 warps of 64 x 32 or 16 of 32 x 32.
+// Small merges of the low tree levels use 64 x 64 tiles.
 inline int launch_dgemm(const uint64_t *A, const uint64_t *B, const uint64_t *C, int nb, int m, int n, int k, int64_t lda,
                         int64_t ldb, int64_t ldc, int sm_count, cudaStream_t st) {
-    const int64_t big = (int64_t)((n + 127) / 128) * ((m + 127) / 128) * nb;
-    if (m >= 96 && n >= 96 && big >= sm_count) {
+    const int64_t big = (int64_t)((n + 63) / 64) * ((m + 127) / 128) * nb;
+    if (m >= 96 && n >= 48 && big >= sm_count) {
 #if AH_GEMM_VARIANT == 1
         return launch_dgemm_tile<128, 128, 2, 4>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);     // 8 warps of 64 x 32
-#elif AH_GEMM_VARIANT == 2
-        return launch_dgemm_tile<128, 64, 2, 4>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);      // 8 warps of 64 x 16, two CTAs per SM
+#elif AH_GEMM_VARIANT == 0
+        return launch_dgemm_tile<128, 128, 4, 4>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);     // 16 warps of 32 x 32
 #else
-        return launch_dgemm_tile<128, 128, 4, 4>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);
+        return launch_dgemm_tile<128, 64, 2, 4>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);      // 8 warps of 64 x 16, two CTAs per SM
 #endif
     }
     return launch_dgemm_tile<64, 64, 2, 4>(A, B, C, nb, m, n, k, lda, ldb, ldc, st);

@@ -341,7 +341,7 @@ struct BisectShared {
     alignas(8) unsigned long long empty[BS];
     alignas(16) double2 hot[BJ];   // (sigma, m) of every slot for the coming sweep
     double part[BJ][BW];
-    long long skip[BJ];            // 0-based index of the slot's shift pole, -1: none (idle slot, or Remedy-3 round)
+    int skip[BJ];                  // 0-based index of the slot's shift pole, -1: none (idle slot, or Remedy-3 round); N < 2^30
     int act[BJ];                   // coming sweep: 1 slot is bisecting, 2 slot waits for its ticket, 0 slot has retired
     double save[BJ];               // accumulator of slot j saved by the one thread that owns its shift pole
     // speculative tail (see k_bisect): helpers of leader slot j for the coming sweep and the bisection points they evaluate
@@ -718,7 +718,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             if (lane == 0) {
                 const bool act = S.phase == PH_BISECT;
                 sh.hot[warp] = act ? make_double2(S.sigma, S.m) : make_double2(0.0, 0.0);
-                sh.skip[warp] = (act && ROUND == 0) ? (long long)(S.i - 1) : -1;   // the re-shifted sigma_1 is not a pole
+                sh.skip[warp] = (act && ROUND == 0) ? (int)(S.i - 1) : -1;   // the re-shifted sigma_1 is not a pole
                 sh.act[warp] = act ? 1 : (S.phase == PH_PENDING ? 2 : 0);
             }
         }
@@ -764,7 +764,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                             }
                             sh.grp_pt[L][t] = pt;
                             sh.hot[warp] = make_double2(Ls.sigma, pt);
-                            sh.skip[warp] = (long long)(Ls.i - 1);
+                            sh.skip[warp] = (int)(Ls.i - 1);
                         }
                         sh.grpn[warp] = 0;
                     }
@@ -782,13 +782,14 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         int fmin = 0x7fffffff, fmax_ = -1;
 #pragma unroll
         for (int j = 0; j < NSLOT; ++j) {
-            const long long sk = sh.skip[j];
+            const int sk = sh.skip[j];
             const int aj = sh.act[j];
             if (aj == 1) actmask |= 1u << j;
             if (aj == 2) waiting = true;
             if (sk >= 0) {
-                const int t_i = (int)(sk / BTL);
-                const int owner = (int)(((sk % BTL) % (2 * BT)) >> 1);
+                static_assert((BTL & (BTL - 1)) == 0 && BTL % (2 * BT) == 0, "tile / owner of a pole by shifts and masks");
+                const int t_i = sk / BTL;
+                const int owner = (sk & (2 * BT - 1)) >> 1;
                 if (owner == tid) { fixmask |= 1u << j; fmin = min(fmin, t_i); fmax_ = max(fmax_, t_i); }
             }
         }
@@ -845,11 +846,11 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             }
 
             if (fix) {
-                const long long base = (long long)tile * BTL;
+                const int base = tile * BTL;
 #pragma unroll
                 for (int j = 0; j < NSLOT; ++j) {
                     if ((fixmask >> j) & 1u) {
-                        const long long sk = sh.skip[j];
+                        const int sk = sh.skip[j];
                         if (sk / BTL == tile) {
                             double a = sh.save[j];
                             const double2 h = sh.hot[j];

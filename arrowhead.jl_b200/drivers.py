@@ -453,7 +453,7 @@ def tdc_recursive(dv, ev, *, ctx: Context | None = None, rotation="reference"):
     return Eigen(E.values, W)
 
 
-_TDC_BIG = 2048      # merges with at least this many poles go through the fast pipeline one by one
+_TDC_BIG = 1000      # merges with at least this many poles go through the fast pipeline one by one
 
 
 def tdc_device(dv, ev, *, ctx: Context | None = None, vectors="host", rotation="reference"):
@@ -515,7 +515,9 @@ def tdc_device(dv, ev, *, ctx: Context | None = None, vectors="host", rotation="
 
 def _tdc_levels(ctx, dv, ev, n, by_height, height, Q, qbase, s_base, wp_base, _View, vectors, rotation):
     ctx.set_identity(Q.ptr, n, n, n)                                  # leaves: U = [1] in buffer 0
-    lam = {(i, i + 1): dv[i:i + 1] for i in range(n)}                 # eigenvalues of every finished node
+    # eigenvalues of every finished node [lo,hi) live in lam[lo:hi] (node-local order): children are read and the merged
+    # node is written back with index arithmetic over the whole size group -- no per-node Python work (8191 nodes at n = 8192)
+    lam = dv.copy()
     stats = {"levels": 0, "batched_problems": 0, "pipeline_problems": 0, "driver_problems": 0, "gemm_calls": 0, "gemm_flops": 0.0,
              "gemm_shapes": []}
     for h in sorted(by_height):
@@ -541,10 +543,9 @@ def _tdc_levels(ctx, dv, ev, n, by_height, height, Q, qbase, s_base, wp_base, _V
             z[:, :k] = g[: nb * k].reshape(nb, k) * ev[p - 1][:, None]
             if r:
                 z[:, k:] = g[nb * k:].reshape(nb, r) * ev[p][:, None]
-            for b, (lo, hi) in enumerate(nodes):
-                D[b, :k] = lam.pop((lo, lo + k))
-                if r:
-                    D[b, k:] = lam.pop((lo + k + 1, hi))
+            D[:, :k] = lam[cl]
+            if r:
+                D[:, k:] = lam[cr]
             a = dv[p]
             # ---- the arrow driver's host logic (arrowhead3.jl:571-573, 583-623), vectorised over the group
             is_ = np.argsort(-D, axis=1, kind="stable")
@@ -605,9 +606,8 @@ def _tdc_levels(ctx, dv, ev, n, by_height, height, Q, qbase, s_base, wp_base, _V
                 stats["gemm_flops"] += 2.0 * nb * r * m * r
                 stats["gemm_shapes"].append((nb, r, m, r))
             Wp.free()
-            for b, node in enumerate(nodes):
-                lam[node] = L[b]
-    values = lam[(0, n)]
+            lam[los[:, None] + np.arange(m)[None, :]] = L
+    values = lam
     troot = height(n) % 3
     E = Eigen(values, None)
     E.stats = stats
