@@ -51,7 +51,7 @@ EXPORTS = [
     "ah_memcpy_d2h", "ah_memcpy_h2d", "ah_set_identity", "ah_apply_givens_rows", "ah_gather_permuted",
     "ah_scale_rows_phase", "ah_symarrow_eigvals_dd", "ah_symarrow_eigen_batched", "ah_gather_elements", "ah_gather_permuted_batched",
     "ah_copy2d_batched", "ah_dgemm_batched",
-    "ah_measure_fp64_peak", "ah_measure_term_peak", "ah_measure_store_bw",
+    "ah_measure_fp64_peak", "ah_measure_term_peak", "ah_measure_rcp_seed_error", "ah_measure_store_bw",
     "ah_set_async", "ah_wait", "ah_last_gemm_ms", "ah_measure_dmma_peak",
     "ah_multi_create", "ah_multi_destroy", "ah_multi_ndev", "ah_multi_ctx", "ah_multi_last_error", "ah_multi_elapsed_ms",
     "ah_k_partition", "ah_multi_symarrow_eigen", "ah_multi_symdpr1_eigen", "ah_multi_halfarrow_svd",
@@ -111,6 +111,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ah_measure_dmma_peak.argtypes = [vp, _dp, _dp]
     lib.ah_measure_fp64_peak.argtypes = [vp, _dp, _dp]
     lib.ah_measure_term_peak.argtypes = [vp, _dp, _dp]
+    lib.ah_measure_rcp_seed_error.argtypes = [vp, _dp, _dp]
     lib.ah_measure_store_bw.argtypes = [vp, C.c_int64, _dp]
     pp = C.POINTER(vp)
     lib.ah_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
@@ -412,6 +413,12 @@ class Context:
         g, ms = C.c_double(), C.c_double()
         self._check(self.lib.ah_measure_term_peak(self.handle, C.byref(g), C.byref(ms)))
         return g.value, ms.value
+
+    def measure_rcp_seed_error(self):
+        """exhaustive max |1 - x*r| of the MUFU.RCP64H seed and of the corrected reciprocal of the secular term"""
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.ah_measure_rcp_seed_error(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def measure_store_bw(self, nbytes):
         g = C.c_double()

@@ -41,6 +41,7 @@ struct ah_ctx {
     int quantum = -1;           // k_bisect time slice (steps): < 0 automatic, 0 off (tuning knob ARROWHEAD_B200_QUANTUM)
     int window = 2;             // time slicing starts when fewer than window x slots eigenpairs wait (ARROWHEAD_B200_WINDOW)
     int spec = 1;               // speculative tail of k_bisect: idle slots evaluate the next midpoints (ARROWHEAD_B200_SPEC=0: off)
+    int accel = 1;              // certified skipping of bisection steps in k_bisect round 0 (ARROWHEAD_B200_ACCEL=0: plain bisection)
     unsigned bisect_tag = 0;    // per-launch tag of the requeue FIFO entries
     bool res_valid = false;     // dD / dZ still hold the inputs of the last solve (ah_resolve)
     int res_kind = 0;
@@ -264,7 +265,23 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             pad = hD[N - 1] - span;
             if (!std::isfinite(pad)) pad = -1.7976931348623157e308;
         }
+        // A pad's term is w2 * (1/t) with w2 = 0: it must never see t = d (1 - m d) = 0 (0 * Inf = NaN).  1 - m d vanishes
+        // exactly only if m = 1/d is representable, i.e. only if d = dshift(pad, sigma) is a power of two for some shift
+        // sigma in D -- nudge the pad until it is not (checked against every pole).
+        auto pad_shift = [&](double pd, double sg) { return L.kind == KIND_HALF ? (pd - sg) * (pd + sg) : pd - sg; };
+        for (int tries = 0; tries < 64; ++tries) {
+            bool pow2 = false;
+            for (int64_t l = 0; l < N && !pow2; ++l) {
+                int ex;
+                pow2 = std::fabs(std::frexp(pad_shift(pad, hD[l]), &ex)) == 0.5;
+            }
+            if (!pow2) break;
+            pad = (L.kind == KIND_HALF) ? std::nextafter(pad, 0.0) : std::nextafter(pad, -INFINITY);
+        }
         for (int64_t l = N; l < Np; ++l) { hPadD[l] = pad; hPadW[l] = 0.0; hPadW2[l] = 0.0; }
+        // |dshift(D_l, sigma)| over all poles (pads included) and all shifts
+        P.dbound = (L.kind == KIND_HALF) ? hD[0] * hD[0] : (hD[0] - pad);
+        if (!(P.dbound > 0.0) || !std::isfinite(P.dbound)) P.dbound = 0.0;
         if ((rc = ensure(ctx, ctx->dD, 3 * Np * 8))) return rc;
         AH_CUDA(cudaEventRecord(ctx->ev[0], st));
         AH_CUDA(cudaMemcpyAsync(ctx->dD.p, ctx->hIn, 3 * Np * 8, cudaMemcpyHostToDevice, st));
@@ -323,7 +340,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         O.status = carve<int32_t>(p, cnt);
     }
     if ((rc = ensure(ctx, ctx->dList, cnt * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->dKs, (size_t)cnt * sizeof(ah::KState)))) return rc;
+    if ((rc = ensure(ctx, ctx->dKs, (size_t)cnt * (sizeof(ah::KState) + sizeof(ah::KExtra))))) return rc;   // KState[cnt] | KExtra[cnt]
     if ((rc = ensure(ctx, ctx->dRList, cnt * 8))) return rc;
     if ((rc = ensure(ctx, ctx->dCount, 2048))) return rc;
     {   // requeue FIFO of k_bisect's time slicing; entries carry a per-launch tag, so it is cleared only when (re)allocated
@@ -415,7 +432,8 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                 ctx->bisect_tag = 1;
             }
             rc = ah::launch_bisect(L.kind, 0, P, Oc, ks, kb, cc, dlist, rlist, dcount, (unsigned long long *)ctx->dQueue.p,
-                                   (long long)(ctx->dQueue.cap / 8), ctx->bisect_tag, ctx->quantum, ctx->window, ctx->spec, ctx->sm_count, st);
+                                   (long long)(ctx->dQueue.cap / 8), ctx->bisect_tag, ctx->quantum, ctx->window, ctx->spec, ctx->sm_count, st,
+                                   (ah::KExtra *)(ks + cnt), ctx->accel);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect launch");
             ctx->stats.launches += 2;   // k_prep, k_bisect round 0
             AH_CUDA(cudaEventRecord(E[2], st));
@@ -652,6 +670,30 @@ __global__ void k_copy2d_batched(const uint64_t *__restrict__ dptr, int64_t ldd,
         reinterpret_cast<double *>(dptr[b])[c * ldd + r] = reinterpret_cast<const double *>(sptr[b])[c * lds + r];
     }
 }
+// Exhaustive accuracy of the reciprocal seed (rcp.approx.ftz.f64 = MUFU.RCP64H looks at the upper 32 bits of its operand
+// only): every pattern of the 20 mantissa bits of the high word x {low word 0, low word all ones} x both signs x a few
+// exponents; out[0] = max |1 - x r0| (exact: one FMA), out[1] = max |1 - x rcp_fast(x)| (the corrected reciprocal of the
+// secular term) as bit patterns of non-negative doubles.
+__global__ void k_rcp_seed_error(unsigned long long *out) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;          // 2^20 mantissa patterns x 2 low words x 2 signs
+    const unsigned hi20 = idx & 0xfffffu, lowsel = (idx >> 20) & 1u, neg = (idx >> 21) & 1u;
+    const int exps[5] = {1023, 1023 - 500, 1023 + 700, 1, 2045};
+    double worst0 = 0.0, worst1 = 0.0;
+    for (int q = 0; q < 5; ++q) {
+        const unsigned long long bits = ((unsigned long long)neg << 63) | ((unsigned long long)exps[q] << 52) | ((unsigned long long)hi20 << 32) |
+                                        (lowsel ? 0xffffffffull : 0ull);
+        const double x = __longlong_as_double((long long)bits);
+        const double r0 = ah::rcp_seed(x);
+        const double e0 = fabs(__fma_rn(-x, r0, 1.0));
+        const double e1 = fabs(__fma_rn(-x, ah::rcp_fast(x), 1.0));
+        if (q < 3 || (r0 != 0.0 && fabs(r0) <= 1.7976931348623157e308)) {   // (the extreme exponents only where the reciprocal is a normal number)
+            worst0 = fmax(worst0, e0);
+            worst1 = fmax(worst1, e1);
+        }
+    }
+    atomicMax(out, (unsigned long long)__double_as_longlong(worst0));
+    atomicMax(out + 1, (unsigned long long)__double_as_longlong(worst1));
+}
 template <int NC>
 __global__ void k_scale_rows_phase(double *dst, int64_t ldd, const double *__restrict__ src, int64_t lds,
                                    const double *__restrict__ phase, int64_t nrows, int64_t ncols) {
@@ -733,6 +775,7 @@ int ah_create(ah_ctx **pctx, int device) {
     if (const char *q = getenv("ARROWHEAD_B200_QUANTUM")) ctx->quantum = atoi(q);
     if (const char *q = getenv("ARROWHEAD_B200_WINDOW")) ctx->window = std::max(1, atoi(q));
     if (const char *q = getenv("ARROWHEAD_B200_SPEC")) ctx->spec = atoi(q) != 0;
+    if (const char *q = getenv("ARROWHEAD_B200_ACCEL")) ctx->accel = atoi(q) != 0;
     if ((e = cudaSetDevice(device)) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaSetDevice"); }
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -1259,6 +1302,21 @@ int ah_measure_term_peak(ah_ctx *ctx, double *gterms_per_s, double *elapsed_ms) 
     AH_CUDA(cudaGetLastError());
     *gterms_per_s = (double)threads * blocks * (double)iters * 32.0 / (best * 1e-3) / 1e9;
     if (elapsed_ms) *elapsed_ms = best;
+    return AH_OK;
+}
+int ah_measure_rcp_seed_error(ah_ctx *ctx, double *seed_err, double *corrected_err) {
+    if (!ctx || !seed_err) return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->dCount, 2048))) return rc;
+    AH_CUDA(cudaMemsetAsync(ctx->dCount.p, 0, 16, ctx->stream));
+    k_rcp_seed_error<<<(1u << 22) / 256, 256, 0, ctx->stream>>>((unsigned long long *)ctx->dCount.p);
+    AH_CUDA(cudaGetLastError());
+    unsigned long long h[2];
+    AH_CUDA(cudaMemcpyAsync(h, ctx->dCount.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    AH_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(seed_err, &h[0], 8);
+    if (corrected_err) std::memcpy(corrected_err, &h[1], 8);
     return AH_OK;
 }
 int ah_measure_store_bw(ah_ctx *ctx, int64_t bytes, double *gb_per_s) {

@@ -54,6 +54,15 @@ struct KState {   // 128 bytes per eigenpair
 // Remedy-3 round (k_rem3_prep -> k_bisect round 1) re-uses the record: sigma := sigma_1 (HalfArrow: its
 // square root; the squared shift is parked in `lambda`), b := rho, left/right := DPR1 bracket, nu1 := new nu_1.
 static_assert(sizeof(KState) == 128, "KState layout");
+// Certified-bracket state of the accelerated bisection (k_bisect<..., ACCEL>), parked here when an eigenpair is time-sliced
+struct KExtra {   // 64 bytes per eigenpair
+    double lo, hi;              // certified: every grid midpoint <= lo decides "left", every one >= hi decides "right"
+    double hx1, hF1, hx2, hF2;  // the last two evaluated points and their F values (secant on (m - pole) F(m))
+    double pole;                // the pole end of the initial bracket
+    int8_t nhist, probing, nprobe, nfail;
+    int32_t pad_;
+};
+static_assert(sizeof(KExtra) == 64, "KExtra layout");
 
 // ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -333,6 +342,9 @@ struct BSlot {   // cold per-slot state, touched by warp j only
     unsigned long long ticket;    // PH_PENDING: the work ticket this slot is waiting on
     double sigma, wz2, b, left, right, m, nu1, Kb, Kz;
     double knu0, krho, sig2;   // round 1: first K_nu (HalfArrow keeps it), K_rho, squared shift (HalfArrow)
+    // accelerated bisection (ACCEL): the point the coming sweep evaluates (the grid midpoint m or a probe), certified bounds, history
+    double x, lo, hi, hx1, hF1, hx2, hF2, pole;
+    int nhist, probing, nprobe, nfail, cert;
 };
 struct BisectShared {
     alignas(128) double tileD[BS][BTL];
@@ -465,12 +477,32 @@ __device__ __forceinline__ unsigned long long ld_volatile(const unsigned long lo
 // interleaving of the chains and costs more than it saves), so a block of fewer than 8 eigenpairs per CTA runs with
 // 7 or 6 slots.  Round 1 is the exception: its list is ~1 % of the block, slot j of a CTA is used only while
 // j * CTAs < cnt (which spreads the list over all CTAs) and the sweep skips the unused slots.
-template <int KIND, int ROUND, int NSLOT>
+//
+// ACCEL (round 0): certified skipping of bisection steps.  The result of a bisection is the final bracket, i.e. the cell of
+// the dyadic grid  m = fl((l + r)/2)  that the computed decisions  F7(m) > 0  lead to.  Most of these ~54 decisions are
+// known without evaluating F7(m): F is strictly decreasing on the bracket (the bracket lies outside all poles of the
+// inverse, so every secular term has the same sign), and a sweep at ANY point x bounds the computed sum at every grid
+// point on one side of x:
+//   * same sign  =>  the computed sum S7 and the exact sum S_X of the computed terms' exact values satisfy
+//     |S7 - S_X| <= theta |S_X|, theta = (terms per thread + reduction depth + 2) * 2^-53  (<= 1.6 ulp per reciprocal, one rounding
+//     per accumulation; no cancellation), and S_X(m) is monotone in m because every fl operation of a term is;
+//   * the decision  fl(fl(b - m) - fl(fl(S wz^2) + fl(wz^2 / -m))) > 0  is monotone in S and in m for the same reason.
+// Hence if the decision at x comes out "left" for S7(x) (1 +- 2.01 theta) both, F7(m) > 0 at every grid point m <= x ("lo"),
+// and likewise "right" for every m >= x ("hi").  Grid points outside (lo, hi) are decided for free; grid points inside are
+// evaluated and decided by their own F7(m) exactly as plain bisection would -- the final bracket is bit-identical.
+// Where to evaluate is a heuristic with no influence on the result: the first two sweeps are grid points, then a secant
+// iteration on (m - pole) F(m) (exact for F = alpha + beta/(m - pole)) aims delta = 4 x 2.01 theta scale / |F'| to the side
+// of its root estimate whose certificate is further away, until lo and hi are ~8 delta apart; the rest (the last ~10 grid
+// cells, where F7 is rounding noise) are plain steps.  ~19 sweeps instead of ~54.  Preconditions checked per eigenpair
+// (else plain bisection): no overflow of d (1 - m d) anywhere in the bracket; per launch: N <= 2^21.
+template <int KIND, int ROUND, int NSLOT, int ACCEL>
 __global__ void __launch_bounds__(BT, BCTAS)
 k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *__restrict__ dlist,
          int64_t *__restrict__ rlist, unsigned long long *dcount, unsigned long long *__restrict__ queue, long long qcap,
-         unsigned tag, int quantum, int window, int spec) {
+         unsigned tag, int quantum, int window, int spec, KExtra *__restrict__ kx, double th2) {
     static_assert(NSLOT >= 1 && NSLOT <= BJ && NSLOT <= BW, "one warp per slot");
+    static_assert(!(ACCEL && ROUND != 0), "the accelerated bisection is round 0's");
+    if (ACCEL) spec = 0;   // (the helper slots of the speculative tail evaluate grid midpoints only)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BisectShared &sh = *reinterpret_cast<BisectShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -591,7 +623,99 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                 __syncwarp();
                 return goleft ? 1 : 0;
             };
-            if (!first && S.phase == PH_BISECT) {
+            // ACCEL: the sweep evaluated S.x (the grid midpoint S.m or a probe).  Certificates, history, and -- at a grid
+            // point -- the bisection step itself.
+            auto accel_step = [&]() -> int {
+                double sum = (lane < BW) ? sh.part[warp][lane] : 0.0;
+#pragma unroll
+                for (int o = BW / 2; o > 0; o >>= 1) {
+                    const double p = __shfl_xor_sync(0xffffffffu, sum, o);
+                    sum = (lane & o) ? __dadd_rn(p, sum) : __dadd_rn(sum, p);
+                }
+                int rcode = 0;
+                if (lane == 0) {
+                    const double x = S.x, m = S.m;
+                    const bool grid = (x == m);
+                    if (!(fabs(sum) <= 1.7976931348623157e308)) {   // NaN / Inf sweep
+                        if (grid) {             // as in plain bisection: k_full redoes the eigenpair with exact divisions
+                            ks[S.k - kbase].flag = KS_HANDOFF;
+                            dlist[atomicAdd(dcount, 1ull)] = S.k;
+                            if (quantum > 0) atomicAdd(dcount + 5, 1ull);
+                            S.phase = PH_FREE;
+                            rcode = -1;
+                        } else {
+                            S.probing = 0;      // a probe that cannot be used
+                        }
+                    } else {
+                        const double wz2 = S.wz2;
+                        const double bm = __dadd_rn(S.b, -x);
+                        const double c = (KIND != KIND_DPR1) ? __ddiv_rn(wz2, __dadd_rn(0.0, -x)) : 0.0;
+                        auto Fof = [&](double s) {
+                            double t = __dmul_rn(s, wz2);
+                            if (KIND != KIND_DPR1) t = __dadd_rn(t, c);
+                            return __dadd_rn(bm, -t);                                  // arrowhead3.jl:696-701
+                        };
+                        const double F = Fof(sum);
+                        if (S.cert && fabs(sum) > 1.0e-250) {
+                            const bool la = Fof(__dmul_rn(sum, 1.0 + th2)) > 0.0, lb = Fof(__dmul_rn(sum, 1.0 - th2)) > 0.0;
+                            if (la && lb) S.lo = fmax(S.lo, x);
+                            else if (!la && !lb) S.hi = fmin(S.hi, x);
+                            else if (!grid && ++S.nfail >= 2) S.probing = 0;
+                        }
+                        S.hx1 = S.hx2; S.hF1 = S.hF2; S.hx2 = x; S.hF2 = F;
+                        if (S.nhist < 2) S.nhist += 1;
+                        if (grid) { if (F > 0.0) S.left = m; else S.right = m; }
+                    }
+                    S.steps += 1;
+                    S.q += 1;
+                }
+                rcode = __shfl_sync(0xffffffffu, rcode, 0);
+                __syncwarp();
+                return rcode;
+            };
+            // ACCEL: grid points decided by the certificates cost nothing; S.m = the first grid midpoint that is not
+            auto accel_descend = [&]() {
+                if (lane == 0) {
+                    double l = S.left, r = S.right;
+                    const double lo = S.lo, hi = S.hi;
+                    double m = (l + r) / 2.0;
+                    while ((r - l) > 2.0 * kEps * fmax(fabs(l), fabs(r))) {
+                        if (m <= lo) l = m;
+                        else if (m >= hi) r = m;
+                        else break;
+                        m = (l + r) / 2.0;
+                    }
+                    S.left = l; S.right = r; S.m = m;
+                }
+                __syncwarp();
+            };
+            // ACCEL: where the coming sweep evaluates F -- the grid midpoint, or a probe that tightens lo / hi
+            auto accel_choose = [&]() {
+                if (lane == 0) {
+                    double x = S.m;
+                    if (S.probing && S.nhist >= 2 && S.nprobe < 24) {
+                        const double x1 = S.hx1, F1 = S.hF1, x2 = S.hx2, F2 = S.hF2, p = S.pole;
+                        const double a_ = fmax(S.lo, S.left), b_ = fmin(S.hi, S.right);
+                        const double dx = x2 - x1;
+                        const double slope = fabs((F2 - F1) * rcp_fast(dx));
+                        const double bm = S.b - x2;
+                        const double scale = fabs(bm) + fabs(F2 - bm);
+                        const double delta = 4.0 * th2 * scale * rcp_fast(slope);
+                        if (!((b_ - a_) > 8.0 * delta)) S.probing = 0;          // (also when delta is NaN)
+                        else {
+                            const double G1 = (x1 - p) * F1, G2 = (x2 - p) * F2;
+                            const double xs = x2 - G2 * dx * rcp_fast(G2 - G1);
+                            const double xp = ((xs - a_) > (b_ - xs)) ? xs - delta : xs + delta;
+                            if (xp > a_ && xp < b_) { x = xp; S.nprobe += 1; }
+                        }
+                    }
+                    S.x = x;
+                }
+                __syncwarp();
+            };
+            if (ACCEL) {
+                if (!first && S.phase == PH_BISECT) accel_step();
+            } else if (!first && S.phase == PH_BISECT) {
                 const int g1 = bisection_step(warp);
                 // Speculative tail: helper slots (idle slots of this CTA) evaluated F at the midpoints of both halves
                 // (and, with six helpers, of all four quarters) in the same sweep, so the step(s) that the reference
@@ -616,6 +740,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
 #endif
             while (true) {
                 if (S.phase == PH_BISECT) {
+                    if (ACCEL) accel_descend();
                     if (bisect_converged(S)) {   // (the reference tests before the first step, too) -> finalise
                         bisect_finalize<KIND, ROUND>(P, O, ks, S, kbase, dlist, rlist, dcount, lane);
                         __syncwarp();
@@ -644,10 +769,18 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                             swap = __shfl_sync(0xffffffffu, swap, 0);
                             AH_TB(tb_swapchk, tb_n_swapchk);
                         }
-                        if (!swap) break;
+                        if (!swap) {
+                            if (ACCEL) accel_choose();
+                            break;
+                        }
                         if (lane == 0) {
                             KState &G = ks[S.k - kbase];
                             G.left = S.left; G.right = S.right; G.steps = S.steps;
+                            if (ACCEL) {
+                                KExtra &X = kx[S.k - kbase];
+                                X.lo = S.lo; X.hi = S.hi; X.hx1 = S.hx1; X.hF1 = S.hF1; X.hx2 = S.hx2; X.hF2 = S.hF2; X.pole = S.pole;
+                                X.nhist = (int8_t)S.nhist; X.probing = (int8_t)S.probing; X.nprobe = (int8_t)S.nprobe; X.nfail = (int8_t)S.nfail;
+                            }
                             __threadfence();
                             const unsigned long long r = atomicAdd(dcount + 4, 1ull);
                             *reinterpret_cast<volatile unsigned long long *>(queue + r) =
@@ -709,6 +842,23 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                     else { S.wz2 = 1.0; S.knu0 = G.knu; S.krho = G.krho; S.sig2 = G.lambda; }
                     S.q = 0;
                     S.phase = PH_BISECT;
+                    if (ACCEL) {
+                        // no overflow of t = d (1 - m d) for any m of the bracket and any pole (pads included): |d| <= P.dbound
+                        S.cert = (fmax(fabs(S.left), fabs(S.right)) * P.dbound * P.dbound < 1.0e300) ? 1 : 0;
+                        if (S.steps > 0) {   // time-sliced before: its certificates and history come along
+                            const KExtra &X = kx[col];
+                            S.lo = __ldcg(&X.lo); S.hi = __ldcg(&X.hi); S.hx1 = __ldcg(&X.hx1); S.hF1 = __ldcg(&X.hF1);
+                            S.hx2 = __ldcg(&X.hx2); S.hF2 = __ldcg(&X.hF2); S.pole = __ldcg(&X.pole);
+                            const int pk = __ldcg(reinterpret_cast<const int *>(&X.nhist));
+                            S.nhist = (int)(int8_t)(pk & 0xff); S.probing = (int)(int8_t)((pk >> 8) & 0xff);
+                            S.nprobe = (int)(int8_t)((pk >> 16) & 0xff); S.nfail = (int)(int8_t)((pk >> 24) & 0xff);
+                        } else {
+                            S.lo = -INFINITY; S.hi = INFINITY; S.hx1 = 0.0; S.hF1 = 0.0; S.hx2 = 0.0; S.hF2 = 0.0;
+                            S.pole = S.sideR ? S.left : S.right;
+                            S.nhist = 0; S.probing = S.cert; S.nprobe = 0; S.nfail = 0;
+                        }
+                        S.x = S.m;
+                    }
                 }
                 __syncwarp();
 #ifdef AH_DIAG_TIMING
@@ -717,7 +867,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
             }
             if (lane == 0) {
                 const bool act = S.phase == PH_BISECT;
-                sh.hot[warp] = act ? make_double2(S.sigma, S.m) : make_double2(0.0, 0.0);
+                sh.hot[warp] = act ? make_double2(S.sigma, ACCEL ? S.x : S.m) : make_double2(0.0, 0.0);
                 sh.skip[warp] = (act && ROUND == 0) ? (int)(S.i - 1) : -1;   // the re-shifted sigma_1 is not a pole
                 sh.act[warp] = act ? 1 : (S.phase == PH_PENDING ? 2 : 0);
             }
@@ -1228,7 +1378,8 @@ inline int configure_pipe_kernels() {
     const int smem = (int)sizeof(BisectShared);
     cudaError_t e;
 #define AH_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)e
-#define AH_SET_KIND(KD) AH_SET_SMEM((k_bisect<KD, 0, 8>)); AH_SET_SMEM((k_bisect<KD, 0, 7>)); AH_SET_SMEM((k_bisect<KD, 0, 6>)); AH_SET_SMEM((k_bisect<KD, 1, 8>))
+#define AH_SET_KIND(KD) AH_SET_SMEM((k_bisect<KD, 0, 8, 0>)); AH_SET_SMEM((k_bisect<KD, 0, 7, 0>)); AH_SET_SMEM((k_bisect<KD, 0, 6, 0>)); AH_SET_SMEM((k_bisect<KD, 1, 8, 0>)); \
+    AH_SET_SMEM((k_bisect<KD, 0, 8, 1>)); AH_SET_SMEM((k_bisect<KD, 0, 7, 1>)); AH_SET_SMEM((k_bisect<KD, 0, 6, 1>))
     AH_SET_KIND(KIND_ARROW); AH_SET_KIND(KIND_DPR1); AH_SET_KIND(KIND_HALF);
 #undef AH_SET_KIND
 #undef AH_SET_SMEM
@@ -1252,9 +1403,16 @@ inline size_t bisect_queue_entries(int64_t cnt) { return (size_t)cnt * 24 + 8192
 
 // quantum: steps an eigenpair keeps its slot while others wait (0: no time slicing, < 0: chosen here);
 // window: time slicing starts when fewer than window x (all slots) eigenpairs are waiting; tag: unique per launch, != 0
+// relative bound used by the certificates of the accelerated bisection: 2.01 x ((terms per thread) + 8 reduction levels +
+// reciprocal (<= 1.6 ulp) + slack) x 2^-53; 0 = not available (N > 2^21: the bound would no longer be small)
+inline double bisect_th2(const Problem &P) {
+    if (P.N > ((int64_t)1 << 21) || !(P.dbound > 0.0)) return 0.0;
+    const double terms = (double)(P.Np / BTL) * BE;
+    return 2.01 * (terms + 16.0) * 1.1102230246251565e-16;
+}
 inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O, KState *ks, int64_t kbase, int64_t cnt,
                          int64_t *dlist, int64_t *rlist, unsigned long long *dcount, unsigned long long *queue, long long qcap,
-                         unsigned tag, int quantum, int window, int spec, int sm_count, cudaStream_t st) {
+                         unsigned tag, int quantum, int window, int spec, int sm_count, cudaStream_t st, KExtra *kx = nullptr, int accel = 0) {
     const int smem = (int)sizeof(BisectShared);
     const int64_t cap = (int64_t)sm_count * BCTAS;
     // Round 0: 8 slots per CTA unless the block has fewer than 8 (7) eigenpairs per CTA of a full grid -- then 7 (6)
@@ -1272,17 +1430,23 @@ inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O
         // and nothing ever waits when every eigenpair has a slot of its own from the start
         quantum = (cnt <= (int64_t)grid * nslot) ? 0 : (int)std::min<int64_t>(32, std::max<int64_t>(8, 128 / std::max<int64_t>(1, ntiles)));
     }
-#define AH_LAUNCH_BISECT(KD, RD, NS) k_bisect<KD, RD, NS><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount, queue, qcap, tag, quantum, window, spec)
-#define AH_LAUNCH_KIND(RD, NS)                                          \
-    switch (kind) {                                                     \
-        case KIND_ARROW: AH_LAUNCH_BISECT(KIND_ARROW, RD, NS); break;   \
-        case KIND_DPR1: AH_LAUNCH_BISECT(KIND_DPR1, RD, NS); break;     \
-        default: AH_LAUNCH_BISECT(KIND_HALF, RD, NS); break;            \
+    const double th2 = (round == 0 && accel && kx) ? bisect_th2(P) : 0.0;
+#define AH_LAUNCH_BISECT(KD, RD, NS, AC) k_bisect<KD, RD, NS, AC><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount, queue, qcap, tag, quantum, window, spec, kx, th2)
+#define AH_LAUNCH_KIND(RD, NS, AC)                                          \
+    switch (kind) {                                                         \
+        case KIND_ARROW: AH_LAUNCH_BISECT(KIND_ARROW, RD, NS, AC); break;   \
+        case KIND_DPR1: AH_LAUNCH_BISECT(KIND_DPR1, RD, NS, AC); break;     \
+        default: AH_LAUNCH_BISECT(KIND_HALF, RD, NS, AC); break;            \
     }
-    if (round == 1) { AH_LAUNCH_KIND(1, 8) }
-    else if (nslot == 8) { AH_LAUNCH_KIND(0, 8) }
-    else if (nslot == 7) { AH_LAUNCH_KIND(0, 7) }
-    else { AH_LAUNCH_KIND(0, 6) }
+    if (round == 1) { AH_LAUNCH_KIND(1, 8, 0) }
+    else if (th2 > 0.0) {
+        if (nslot == 8) { AH_LAUNCH_KIND(0, 8, 1) }
+        else if (nslot == 7) { AH_LAUNCH_KIND(0, 7, 1) }
+        else { AH_LAUNCH_KIND(0, 6, 1) }
+    }
+    else if (nslot == 8) { AH_LAUNCH_KIND(0, 8, 0) }
+    else if (nslot == 7) { AH_LAUNCH_KIND(0, 7, 0) }
+    else { AH_LAUNCH_KIND(0, 6, 0) }
 #undef AH_LAUNCH_KIND
 #undef AH_LAUNCH_BISECT
     return (int)cudaGetLastError();

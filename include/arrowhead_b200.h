@@ -269,6 +269,10 @@ int ah_measure_fp64_peak(ah_ctx *ctx, double *ginstr_per_s, double *elapsed_ms);
 /* The same for the instruction mix of the bisection term (7 FP64-pipe instructions + 1 MUFU.RCP64H per secular term,
  * 32 independent terms per thread and iteration, registers only): 1e9 terms/s.  The ceiling of k_bisect's inner block. */
 int ah_measure_term_peak(ah_ctx *ctx, double *gterms_per_s, double *elapsed_ms);
+/* Exhaustive accuracy of the reciprocal seed the secular term starts from (MUFU.RCP64H: all 2^20 high-word mantissa
+ * patterns x low word 0 / all ones x both signs x several exponents): max |1 - x*r0|, and the same for the corrected
+ * reciprocal of the term.  The certificates of the accelerated bisection assume seed_err <= 2^-18. */
+int ah_measure_rcp_seed_error(ah_ctx *ctx, double *seed_err, double *corrected_err);
 /* streaming store of `bytes` to device memory: GB/s */
 int ah_measure_store_bw(ah_ctx *ctx, int64_t bytes, double *gb_per_s);
 

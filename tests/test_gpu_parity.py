@@ -162,8 +162,10 @@ def test_remedy_branches_are_exercised(gpu_ctx, oracle_lib):
     G = gpu_ctx.symarrow(D, z, a, vectors=False)
     assert G.stats["n_rem3"] > 0 and G.stats["n_fast"] > 900      # Remedy 3 runs as round 1 of the fast path
     O = oracle_lib.symarrow(D, z, a, _tau(999), vectors=False)
-    assert np.array_equal(G.steps > 80, O.steps > 80)                    # same k's took the Remedy-3 detour
-    assert abs(int(G.steps.sum()) - int(O.steps.sum())) <= 0.002 * O.steps.sum()
+    assert np.array_equal((G.status & 0x200) != 0, O.steps > 80)         # same k's took the Remedy-3 detour (AH_BR_REM3)
+    # `steps` counts the O(N) sweeps the GPU evaluated: the accelerated bisection decides most grid points of the
+    # reference's ~54 steps from certified bounds and must need well under half of them
+    assert 10 * G.lam.size < int(G.steps.sum()) < 0.5 * O.steps.sum()
 
 
 def test_partial_k_range_and_sharding(gpu_ctx):
