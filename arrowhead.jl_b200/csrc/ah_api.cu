@@ -270,18 +270,18 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         // sigma in D -- nudge the pad until it is not (checked against every pole).
         auto pad_shift = [&](double pd, double sg) { return L.kind == KIND_HALF ? (pd - sg) * (pd + sg) : pd - sg; };
         for (int tries = 0; tries < 64; ++tries) {
-            bool pow2 = false;
-            for (int64_t l = 0; l < N && !pow2; ++l) {
-                int ex;
-                pow2 = std::fabs(std::frexp(pad_shift(pad, hD[l]), &ex)) == 0.5;
+            uint64_t hit = 0;                       // (branch-free: the loop vectorises)
+            for (int64_t l = 0; l < N; ++l) {
+                const double d = pad_shift(pad, hD[l]);
+                uint64_t bits;
+                std::memcpy(&bits, &d, 8);
+                hit |= (uint64_t)((bits & 0x000fffffffffffffull) == 0);
             }
-            if (!pow2) break;
+            if (!hit) break;
             pad = (L.kind == KIND_HALF) ? std::nextafter(pad, 0.0) : std::nextafter(pad, -INFINITY);
         }
         for (int64_t l = N; l < Np; ++l) { hPadD[l] = pad; hPadW[l] = 0.0; hPadW2[l] = 0.0; }
-        // |dshift(D_l, sigma)| over all poles (pads included) and all shifts
-        P.dbound = (L.kind == KIND_HALF) ? hD[0] * hD[0] : (hD[0] - pad);
-        if (!(P.dbound > 0.0) || !std::isfinite(P.dbound)) P.dbound = 0.0;
+
         if ((rc = ensure(ctx, ctx->dD, 3 * Np * 8))) return rc;
         AH_CUDA(cudaEventRecord(ctx->ev[0], st));
         AH_CUDA(cudaMemcpyAsync(ctx->dD.p, ctx->hIn, 3 * Np * 8, cudaMemcpyHostToDevice, st));
@@ -451,9 +451,9 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                     AH_CUDA(cudaStreamWaitEvent(rs, ctx->ev_fork, 0));
                 }
                 AH_CUDA(cudaEventRecord(SE[0], rs));
-                rc = ah::launch_rem3_prep(L.kind, P, Oc, ks, kb, guess, rlist, dlist, dcount, ctx->sm_count, rs);
+                rc = ah::launch_rem3_prep(L.kind, P, Oc, ks, kb, guess, rlist, dlist, dcount, ctx->sm_count, rs, ctx->accel);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_rem3_prep launch");
-                rc = ah::launch_bisect(L.kind, 1, P, Oc, ks, kb, guess, dlist, rlist, dcount, nullptr, 0, 0u, 0, 0, 0, ctx->sm_count, rs);
+                rc = ah::launch_bisect(L.kind, 1, P, Oc, ks, kb, guess, dlist, rlist, dcount, nullptr, 0, 0u, 0, 0, 0, ctx->sm_count, rs, nullptr, ctx->accel);
                 if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_bisect round 1 launch");
                 AH_CUDA(cudaEventRecord(SE[1], rs));
                 ctx->stats.launches += 2;

@@ -31,7 +31,6 @@ struct Problem {
     const double *w2;  // [Np] w_l^2 (fast path)
     int64_t Np;        // D, w, w2 are padded to Np poles (multiple of the fast path's tile); pads: weight 0, D = pad
     double pad;        // pad pole: strictly below every real pole; pad - D_l is never a power of two (1 - m d never cancels exactly there)
-    double dbound;     // >= |dshift(D_l, sigma)| for every pole l (pads included) and every shift sigma in D; 0: unknown
     const double *z;   // [N] half only: the original z (double-double branch needs it)
     double a;          // arrow: arrow top; dpr1: rho (>0)
     double maxabs_w;   // max_l |w_l|

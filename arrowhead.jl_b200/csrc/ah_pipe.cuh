@@ -453,6 +453,125 @@ __device__ __forceinline__ void bisect_finalize(const Problem &P, const Outputs 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Accelerated bisection (see the comment above k_bisect): certificates, free descent of the dyadic grid, probe points.
+// All of it is scalar work of one thread on a slot's state; the sweeps themselves do not change.
+//
+// The decision of one bisection step as a monotone function of the sweep's sum: goleft <=> value > 0, in exactly the
+// reference's operation order (round 0: arrowhead3.jl:696-701 on the inverse arrow; round 1: :736-740 on the DPR1 inverse).
+template <int KIND, int ROUND>
+struct StepDecision {
+    double bm, c, wz2, b, sgn;
+    __device__ __forceinline__ StepDecision(const BSlot &S, double x) {
+        if (ROUND == 0) {
+            wz2 = S.wz2; b = S.b; sgn = 1.0;
+            bm = __dadd_rn(S.b, -x);
+            c = (KIND != KIND_DPR1) ? __ddiv_rn(wz2, __dadd_rn(0.0, -x)) : 0.0;
+        } else {
+            wz2 = 1.0; b = S.b; bm = 0.0; sgn = sign_jl(S.b);
+            c = (KIND != KIND_DPR1) ? __ddiv_rn(1.0, __dadd_rn(0.0, -x)) : 0.0;
+        }
+    }
+    __device__ __forceinline__ double operator()(double s) const {
+        if (ROUND == 0) {
+            double t = __dmul_rn(s, wz2);
+            if (KIND != KIND_DPR1) t = __dadd_rn(t, c);
+            return __dadd_rn(bm, -t);
+        } else {
+            if (KIND != KIND_DPR1) s = __dadd_rn(s, c);
+            const double F = __dadd_rn(1.0, __dmul_rn(b, s));     // b holds rho
+            return -(sgn * F);
+        }
+    }
+};
+
+// Preconditions of the certificates for one eigenpair: (1) the bracket lies outside ALL poles of the inverse, so that every
+// term of a sweep has the same sign -- always true in round 0 (extreme eigenvalue of the inverse arrow); in round 1 only for
+// the brackets [mx1, mx1 + rho uu] (rho > 0, 'R') and [mn1 + rho uu, mn1] (rho < 0, 'L') of arrowhead3.jl:722-726, the other
+// two lie between the two outermost poles; (2) t = d (1 - m d) cannot overflow for any m of the bracket and any pole, pads
+// included (dshift is monotone in the pole, so the two ends of the padded pole range bound |d|).
+template <int KIND, int ROUND>
+__device__ __forceinline__ int accel_certifiable(const Problem &P, const BSlot &S) {
+    if (ROUND == 1 && !((S.b > 0.0) == (S.sideR != 0))) return 0;
+    const double dmax = fmax(fabs(dshift<KIND>(P.D[0], S.sigma)), fabs(dshift<KIND>(P.pad, S.sigma)));
+    return (fmax(fabs(S.left), fabs(S.right)) * dmax * dmax < 1.0e300) ? 1 : 0;
+}
+__device__ __forceinline__ void accel_reset(BSlot &S, int cert) {
+    S.cert = cert;
+    S.lo = -INFINITY; S.hi = INFINITY; S.hx1 = 0.0; S.hF1 = 0.0; S.hx2 = 0.0; S.hF2 = 0.0;
+    S.pole = S.sideR ? S.left : S.right;
+    S.nhist = 0; S.probing = cert; S.nprobe = 0; S.nfail = 0;
+    S.x = S.m;
+}
+// After a sweep at S.x with the sum `sum` (not NaN): certificates, history, and -- at a grid point -- the bisection step itself.
+template <int KIND, int ROUND>
+__device__ __forceinline__ void accel_update(BSlot &S, double sum, double th2) {
+    const double x = S.x, m = S.m;
+    const bool grid = (x == m);
+    const StepDecision<KIND, ROUND> dec(S, x);
+    const double F = dec(sum);
+    if (S.cert && fabs(sum) > 1.0e-250 && fabs(sum) <= 1.7976931348623157e308) {
+        const bool la = dec(__dmul_rn(sum, 1.0 + th2)) > 0.0, lb = dec(__dmul_rn(sum, 1.0 - th2)) > 0.0;
+        if (la && lb) S.lo = fmax(S.lo, x);
+        else if (!la && !lb) S.hi = fmin(S.hi, x);
+        else if (!grid && ++S.nfail >= 2) S.probing = 0;
+    }
+    if (fabs(F) <= 1.7976931348623157e308) {
+        S.hx1 = S.hx2; S.hF1 = S.hF2; S.hx2 = x; S.hF2 = F;
+        if (S.nhist < 2) S.nhist += 1;
+    } else {
+        S.probing = 0;
+    }
+    if (grid) { if (F > 0.0) S.left = m; else S.right = m; }   // the step plain bisection takes here (an infinite sum included)
+}
+// Grid points decided by the certificates cost nothing; S.m = the first grid midpoint that is not (or the converged bracket's).
+__device__ __forceinline__ void accel_descend(BSlot &S) {
+    double l = S.left, r = S.right;
+    const double lo = S.lo, hi = S.hi;
+    double m = (l + r) / 2.0;
+    while ((r - l) > 2.0 * kEps * fmax(fabs(l), fabs(r))) {
+        if (m <= lo) l = m;
+        else if (m >= hi) r = m;
+        else break;
+        m = (l + r) / 2.0;
+    }
+    S.left = l; S.right = r; S.m = m;
+}
+// Where the coming sweep evaluates F: the grid midpoint, or a probe that tightens lo / hi.  Model through the last two
+// evaluated points: value(m) = L(m) + alpha + gamma / (m - pole), L(m) = b - m in round 0 (the known linear part of the arrow's
+// secular function), 0 in round 1; the probe sits delta = 2 x (certifiable distance) to the side of the model's root whose
+// certificate is further away.  Heuristic only: no influence on the result.
+template <int ROUND>
+__device__ __forceinline__ void accel_choose(BSlot &S, double th2) {
+    double x = S.m;
+    if (S.probing && S.nhist >= 2 && S.nprobe < 24) {
+        const double x1 = S.hx1, F1 = S.hF1, x2 = S.hx2, F2 = S.hF2, p = S.pole;
+        const double a_ = fmax(S.lo, S.left), b_ = fmin(S.hi, S.right);
+        const double slope = fabs((F2 - F1) * rcp_fast(x2 - x1));
+        const double L1 = (ROUND == 0) ? S.b - x1 : 0.0, L2 = (ROUND == 0) ? S.b - x2 : 0.0;
+        const double R1 = F1 - L1, R2 = F2 - L2;
+        const double scale = (ROUND == 0) ? fabs(L2) + fabs(R2) : 1.0 + fabs(sign_jl(S.b) * F2 + 1.0);   // magnitude of the operands of the last addition
+        const double delta = 2.0 * th2 * scale * rcp_fast(slope);
+        if (!((b_ - a_) > 6.0 * delta)) S.probing = 0;          // (also when delta is NaN)
+        else {
+            const double i1 = rcp_fast(x1 - p), i2 = rcp_fast(x2 - p);
+            const double gam = (R1 - R2) * rcp_fast(i1 - i2), alpha = R2 - gam * i2;
+            double xs;
+            if (ROUND == 0) {   // (b + alpha - m)(m - p) + gamma = 0
+                const double B = S.b + alpha + p, C = (S.b + alpha) * p - gam;
+                const double sq = sqrt(B * B - 4.0 * C);
+                const double ra = (B + sq) / 2.0, rb = (B - sq) / 2.0;
+                xs = (ra > a_ && ra < b_) ? ra : rb;
+            } else {
+                xs = p - gam * rcp_fast(alpha);
+            }
+            const double xp = ((xs - a_) > (b_ - xs)) ? xs - delta : xs + delta;
+            if (xp > a_ && xp < b_) { x = xp; S.nprobe += 1; }
+        }
+    }
+    S.x = x;
+}
+
 __device__ __forceinline__ bool bisect_converged(const BSlot &S) {
     return !((S.right - S.left) > 2.0 * kEps * fmax(fabs(S.left), fabs(S.right)));
 }
@@ -501,8 +620,6 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
          int64_t *__restrict__ rlist, unsigned long long *dcount, unsigned long long *__restrict__ queue, long long qcap,
          unsigned tag, int quantum, int window, int spec, KExtra *__restrict__ kx, double th2) {
     static_assert(NSLOT >= 1 && NSLOT <= BJ && NSLOT <= BW, "one warp per slot");
-    static_assert(!(ACCEL && ROUND != 0), "the accelerated bisection is round 0's");
-    if (ACCEL) spec = 0;   // (the helper slots of the speculative tail evaluate grid midpoints only)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BisectShared &sh = *reinterpret_cast<BisectShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -623,10 +740,10 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                 __syncwarp();
                 return goleft ? 1 : 0;
             };
-            // ACCEL: the sweep evaluated S.x (the grid midpoint S.m or a probe).  Certificates, history, and -- at a grid
-            // point -- the bisection step itself.
-            auto accel_step = [&]() -> int {
-                double sum = (lane < BW) ? sh.part[warp][lane] : 0.0;
+            // ACCEL: the sweep evaluated S.x (the grid midpoint S.m or a probe); ps != warp: helper slot ps evaluated the
+            // grid midpoint S.m for this slot (speculative tail)
+            auto accel_step = [&](int ps) -> int {
+                double sum = (lane < BW) ? sh.part[ps][lane] : 0.0;
 #pragma unroll
                 for (int o = BW / 2; o > 0; o >>= 1) {
                     const double p = __shfl_xor_sync(0xffffffffu, sum, o);
@@ -634,10 +751,9 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                 }
                 int rcode = 0;
                 if (lane == 0) {
-                    const double x = S.x, m = S.m;
-                    const bool grid = (x == m);
-                    if (!(fabs(sum) <= 1.7976931348623157e308)) {   // NaN / Inf sweep
-                        if (grid) {             // as in plain bisection: k_full redoes the eigenpair with exact divisions
+                    if (ps != warp) S.x = S.m;
+                    if (sum != sum) {           // NaN sweep
+                        if (S.x == S.m) {       // at a grid point, as in plain bisection: k_full redoes the eigenpair with exact divisions
                             ks[S.k - kbase].flag = KS_HANDOFF;
                             dlist[atomicAdd(dcount, 1ull)] = S.k;
                             if (quantum > 0) atomicAdd(dcount + 5, 1ull);
@@ -647,24 +763,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                             S.probing = 0;      // a probe that cannot be used
                         }
                     } else {
-                        const double wz2 = S.wz2;
-                        const double bm = __dadd_rn(S.b, -x);
-                        const double c = (KIND != KIND_DPR1) ? __ddiv_rn(wz2, __dadd_rn(0.0, -x)) : 0.0;
-                        auto Fof = [&](double s) {
-                            double t = __dmul_rn(s, wz2);
-                            if (KIND != KIND_DPR1) t = __dadd_rn(t, c);
-                            return __dadd_rn(bm, -t);                                  // arrowhead3.jl:696-701
-                        };
-                        const double F = Fof(sum);
-                        if (S.cert && fabs(sum) > 1.0e-250) {
-                            const bool la = Fof(__dmul_rn(sum, 1.0 + th2)) > 0.0, lb = Fof(__dmul_rn(sum, 1.0 - th2)) > 0.0;
-                            if (la && lb) S.lo = fmax(S.lo, x);
-                            else if (!la && !lb) S.hi = fmin(S.hi, x);
-                            else if (!grid && ++S.nfail >= 2) S.probing = 0;
-                        }
-                        S.hx1 = S.hx2; S.hF1 = S.hF2; S.hx2 = x; S.hF2 = F;
-                        if (S.nhist < 2) S.nhist += 1;
-                        if (grid) { if (F > 0.0) S.left = m; else S.right = m; }
+                        accel_update<KIND, ROUND>(S, sum, th2);
                     }
                     S.steps += 1;
                     S.q += 1;
@@ -673,48 +772,27 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                 __syncwarp();
                 return rcode;
             };
-            // ACCEL: grid points decided by the certificates cost nothing; S.m = the first grid midpoint that is not
-            auto accel_descend = [&]() {
-                if (lane == 0) {
-                    double l = S.left, r = S.right;
-                    const double lo = S.lo, hi = S.hi;
-                    double m = (l + r) / 2.0;
-                    while ((r - l) > 2.0 * kEps * fmax(fabs(l), fabs(r))) {
-                        if (m <= lo) l = m;
-                        else if (m >= hi) r = m;
-                        else break;
-                        m = (l + r) / 2.0;
-                    }
-                    S.left = l; S.right = r; S.m = m;
-                }
-                __syncwarp();
-            };
-            // ACCEL: where the coming sweep evaluates F -- the grid midpoint, or a probe that tightens lo / hi
-            auto accel_choose = [&]() {
-                if (lane == 0) {
-                    double x = S.m;
-                    if (S.probing && S.nhist >= 2 && S.nprobe < 24) {
-                        const double x1 = S.hx1, F1 = S.hF1, x2 = S.hx2, F2 = S.hF2, p = S.pole;
-                        const double a_ = fmax(S.lo, S.left), b_ = fmin(S.hi, S.right);
-                        const double dx = x2 - x1;
-                        const double slope = fabs((F2 - F1) * rcp_fast(dx));
-                        const double bm = S.b - x2;
-                        const double scale = fabs(bm) + fabs(F2 - bm);
-                        const double delta = 4.0 * th2 * scale * rcp_fast(slope);
-                        if (!((b_ - a_) > 8.0 * delta)) S.probing = 0;          // (also when delta is NaN)
-                        else {
-                            const double G1 = (x1 - p) * F1, G2 = (x2 - p) * F2;
-                            const double xs = x2 - G2 * dx * rcp_fast(G2 - G1);
-                            const double xp = ((xs - a_) > (b_ - xs)) ? xs - delta : xs + delta;
-                            if (xp > a_ && xp < b_) { x = xp; S.nprobe += 1; }
-                        }
-                    }
-                    S.x = x;
-                }
-                __syncwarp();
-            };
             if (ACCEL) {
-                if (!first && S.phase == PH_BISECT) accel_step();
+                if (!first && S.phase == PH_BISECT) {
+                    int rc = accel_step(warp);
+                    // Speculative tail: helper slots evaluated the midpoints of the next grid level(s) below the point this
+                    // slot's own sweep decided.  Whatever the certificates do not decide anyway and a helper happens to
+                    // have evaluated is a real bisection step taken here, from the helper's sum -- same point, same sum,
+                    // same decision as the sweep this slot would have spent on it.
+                    const int nh = (ROUND == 0) ? sh.grpn[warp] : 0;
+                    for (int lvl = 0; lvl < 2 && nh >= 2 && rc >= 0 && (lvl == 0 || nh >= 6); ++lvl) {
+                        int t = -1;
+                        if (lane == 0) {
+                            accel_descend(S);
+                            if (!bisect_converged(S))
+                                for (int q = 0; q < nh; ++q)
+                                    if (sh.grp_pt[warp][q] == S.m) t = q;
+                        }
+                        t = __shfl_sync(0xffffffffu, t, 0);
+                        if (t < 0) break;
+                        rc = accel_step(sh.grp[warp][t]);
+                    }
+                }
             } else if (!first && S.phase == PH_BISECT) {
                 const int g1 = bisection_step(warp);
                 // Speculative tail: helper slots (idle slots of this CTA) evaluated F at the midpoints of both halves
@@ -740,7 +818,10 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
 #endif
             while (true) {
                 if (S.phase == PH_BISECT) {
-                    if (ACCEL) accel_descend();
+                    if (ACCEL) {
+                        if (lane == 0) accel_descend(S);
+                        __syncwarp();
+                    }
                     if (bisect_converged(S)) {   // (the reference tests before the first step, too) -> finalise
                         bisect_finalize<KIND, ROUND>(P, O, ks, S, kbase, dlist, rlist, dcount, lane);
                         __syncwarp();
@@ -758,7 +839,9 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                         const int left_est = ((__double2hiint(wdt) >> 20) & 0x7ff) - ((__double2hiint(mxb) >> 20) & 0x7ff) + 51;
                         const int qeff = min(quantum, max(qmin, left_est >> AH_QSHIFT));
                         __syncwarp();
-                        if (ROUND == 0 && quantum > 0 && qv >= qeff) {
+                        // (the exterior eigenpairs are never handed back: they need 2-3 times the sweeps of the others -- decades
+                        // of bracket, then ~17 steps inside the rounding noise of F -- and would end the launch alone)
+                        if (ROUND == 0 && quantum > 0 && qv >= qeff && S.k != 1 && S.k != P.N + 1) {
                             if (lane == 0) {
                                 const unsigned long long head = ld_volatile(tickets), nreq = ld_volatile(dcount + 4);
                                 const unsigned long long tail = ucnt + nreq;
@@ -770,7 +853,10 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                             AH_TB(tb_swapchk, tb_n_swapchk);
                         }
                         if (!swap) {
-                            if (ACCEL) accel_choose();
+                            if (ACCEL) {
+                                if (lane == 0) accel_choose<ROUND>(S, th2);
+                                __syncwarp();
+                            }
                             break;
                         }
                         if (lane == 0) {
@@ -807,7 +893,9 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                 long long col = -1;      // >= 0: column of the block, -1: not there yet, -2: never
                 if (lane == 0) {
                     const unsigned long long t = S.ticket;
-                    if (t < ucnt) col = (ROUND == 0) ? (long long)t : (long long)(rlist[t] - kbase);
+                    // round 0: the last column first (if the block ends with k = N+1, that exterior eigenpair is one of the two
+                    // longest bisections of the matrix; k = 1, the other one, is column 0 of its block), then columns 0, 1, ...
+                    if (t < ucnt) col = (ROUND == 0) ? (t == 0 ? (long long)(ucnt - 1) : (long long)(t - 1)) : (long long)(rlist[t] - kbase);
                     else if (quantum == 0) col = -2;
                     else {
                         const unsigned long long r = t - ucnt;
@@ -843,21 +931,15 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                     S.q = 0;
                     S.phase = PH_BISECT;
                     if (ACCEL) {
-                        // no overflow of t = d (1 - m d) for any m of the bracket and any pole (pads included): |d| <= P.dbound
-                        S.cert = (fmax(fabs(S.left), fabs(S.right)) * P.dbound * P.dbound < 1.0e300) ? 1 : 0;
-                        if (S.steps > 0) {   // time-sliced before: its certificates and history come along
+                        accel_reset(S, accel_certifiable<KIND, ROUND>(P, S));
+                        if (ROUND == 0 && S.steps > 0) {   // time-sliced before: its certificates and history come along
                             const KExtra &X = kx[col];
                             S.lo = __ldcg(&X.lo); S.hi = __ldcg(&X.hi); S.hx1 = __ldcg(&X.hx1); S.hF1 = __ldcg(&X.hF1);
                             S.hx2 = __ldcg(&X.hx2); S.hF2 = __ldcg(&X.hF2); S.pole = __ldcg(&X.pole);
                             const int pk = __ldcg(reinterpret_cast<const int *>(&X.nhist));
                             S.nhist = (int)(int8_t)(pk & 0xff); S.probing = (int)(int8_t)((pk >> 8) & 0xff);
                             S.nprobe = (int)(int8_t)((pk >> 16) & 0xff); S.nfail = (int)(int8_t)((pk >> 24) & 0xff);
-                        } else {
-                            S.lo = -INFINITY; S.hi = INFINITY; S.hx1 = 0.0; S.hF1 = 0.0; S.hx2 = 0.0; S.hF2 = 0.0;
-                            S.pole = S.sideR ? S.left : S.right;
-                            S.nhist = 0; S.probing = S.cert; S.nprobe = 0; S.nfail = 0;
                         }
-                        S.x = S.m;
                     }
                 }
                 __syncwarp();
@@ -869,7 +951,10 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                 const bool act = S.phase == PH_BISECT;
                 sh.hot[warp] = act ? make_double2(S.sigma, ACCEL ? S.x : S.m) : make_double2(0.0, 0.0);
                 sh.skip[warp] = (act && ROUND == 0) ? (int)(S.i - 1) : -1;   // the re-shifted sigma_1 is not a pole
-                sh.act[warp] = act ? 1 : (S.phase == PH_PENDING ? 2 : 0);
+                // 1: plain bisection steps (helper slots may evaluate the next grid levels), 3: (ACCEL) still probing -- the
+                // sequence of evaluated points must not depend on whether helpers were around, so none are used --,
+                // 2: waits for its ticket, 0: retired
+                sh.act[warp] = act ? ((ACCEL && S.probing) ? 3 : 1) : (S.phase == PH_PENDING ? 2 : 0);
             }
         }
         first = false;
@@ -886,7 +971,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         if (ROUND == 0 && spec) {
             unsigned busy = 0, idle = 0;
 #pragma unroll
-            for (int j = 0; j < NSLOT; ++j) { if (sh.act[j] == 1) busy |= 1u << j; else idle |= 1u << j; }
+            for (int j = 0; j < NSLOT; ++j) { const int aj = sh.act[j]; if (aj == 1) busy |= 1u << j; else if (aj != 3) idle |= 1u << j; }
             const int nb = __popc(busy), ni = __popc(idle);
             const int h = (nb == 0) ? 0 : (ni >= 6 * nb ? 6 : (ni >= 2 * nb ? 2 : 0));
             if (h) {                                                    // CTA-uniform
@@ -898,7 +983,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                         sh.grpn[warp] = h;
                     } else {
                         const int ri = __popc(idle & ((1u << warp) - 1u));
-                        if (ri < nb * h) {                              // helper number t of leader L
+                        if (((idle >> warp) & 1u) && ri < nb * h) {     // helper number t of leader L
                             const int L = nth_bit(busy, ri / h), t = ri % h;
                             const BSlot &Ls = sh.slot[L];
                             const double l = Ls.left, r = Ls.right, m = Ls.m;
@@ -934,7 +1019,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
         for (int j = 0; j < NSLOT; ++j) {
             const int sk = sh.skip[j];
             const int aj = sh.act[j];
-            if (aj == 1) actmask |= 1u << j;
+            if (aj & 1) actmask |= 1u << j;
             if (aj == 2) waiting = true;
             if (sk >= 0) {
                 static_assert((BTL & (BTL - 1)) == 0 && BTL % (2 * BT) == 0, "tile / owner of a pole by shifts and masks");
@@ -1064,7 +1149,7 @@ static_assert(RT == BT, "the direct bisection reproduces k_bisect's summation or
 template <int KIND>
 __global__ void __launch_bounds__(RT, AH_REM3_MINB)
 k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t *__restrict__ rlist, int64_t *__restrict__ dlist,
-            unsigned long long *dcount) {
+            unsigned long long *dcount, double th2) {
     __shared__ double red[2 * (RT / 32) + 2];
     __shared__ double part2[2][RT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1128,7 +1213,12 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
             __syncthreads();                           // every thread has read G before thread 0 rewrites it in the finalize
             int par = 0;
             bool nanfail = false;
-            while (!bisect_converged(S)) {
+            const bool accel = th2 > 0.0;
+            accel_reset(S, accel ? accel_certifiable<KIND, 1>(P, S) : 0);    // (every thread: identical scalar work)
+            while (true) {
+                if (accel) accel_descend(S);
+                if (bisect_converged(S)) break;
+                if (accel) accel_choose<1>(S, th2); else S.x = S.m;
                 // One CTA per eigenpair: a sweep is latency-bound on the L2 loads unless several tiles are in flight.  The
                 // loads of RU tiles are issued together and the next group is fetched while this one is evaluated; the
                 // terms are still accumulated tile by tile, pair by pair -- k_bisect's order, bit for bit.
@@ -1152,8 +1242,8 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
                         if (tile0 + u < ntiles) {
 #pragma unroll
                             for (int h = 0; h < RH; ++h) {
-                                acc = secular_term_acc(acc, dshift<KIND>(dcur[u][h].x, S.sigma), S.m, wcur[u][h].x);
-                                acc = secular_term_acc(acc, dshift<KIND>(dcur[u][h].y, S.sigma), S.m, wcur[u][h].y);
+                                acc = secular_term_acc(acc, dshift<KIND>(dcur[u][h].x, S.sigma), S.x, wcur[u][h].x);
+                                acc = secular_term_acc(acc, dshift<KIND>(dcur[u][h].y, S.sigma), S.x, wcur[u][h].y);
                             }
                         }
                     }
@@ -1172,6 +1262,17 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
                     sum = (lane & o) ? __dadd_rn(p, sum) : __dadd_rn(sum, p);
                 }
                 sum = __shfl_sync(0xffffffffu, sum, 0);
+                par ^= 1;
+                if (accel) {
+                    S.steps += 1;
+                    if (sum != sum) {
+                        if (S.x == S.m) { nanfail = true; break; }
+                        S.probing = 0;
+                    } else {
+                        accel_update<KIND, 1>(S, sum, th2);
+                    }
+                    continue;
+                }
                 if (sum != sum) { nanfail = true; break; }   // as in k_bisect: k_full redoes this eigenpair
                 const double m = S.m;
                 if (KIND != KIND_DPR1) sum = __dadd_rn(sum, __ddiv_rn(1.0, __dadd_rn(0.0, -m)));
@@ -1179,7 +1280,6 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
                 if (sign_jl(S.b) * F < 0.0) S.left = m; else S.right = m;
                 S.m = (S.left + S.right) / 2.0;
                 S.steps += 1;
-                par ^= 1;
             }
             if (nanfail) {
                 if (tid == 0) { G.flag = KS_HANDOFF; dlist[atomicAdd(dcount, 1ull)] = k; }
@@ -1379,7 +1479,7 @@ inline int configure_pipe_kernels() {
     cudaError_t e;
 #define AH_SET_SMEM(K) if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return (int)e
 #define AH_SET_KIND(KD) AH_SET_SMEM((k_bisect<KD, 0, 8, 0>)); AH_SET_SMEM((k_bisect<KD, 0, 7, 0>)); AH_SET_SMEM((k_bisect<KD, 0, 6, 0>)); AH_SET_SMEM((k_bisect<KD, 1, 8, 0>)); \
-    AH_SET_SMEM((k_bisect<KD, 0, 8, 1>)); AH_SET_SMEM((k_bisect<KD, 0, 7, 1>)); AH_SET_SMEM((k_bisect<KD, 0, 6, 1>))
+    AH_SET_SMEM((k_bisect<KD, 0, 8, 1>)); AH_SET_SMEM((k_bisect<KD, 0, 7, 1>)); AH_SET_SMEM((k_bisect<KD, 0, 6, 1>)); AH_SET_SMEM((k_bisect<KD, 1, 8, 1>))
     AH_SET_KIND(KIND_ARROW); AH_SET_KIND(KIND_DPR1); AH_SET_KIND(KIND_HALF);
 #undef AH_SET_KIND
 #undef AH_SET_SMEM
@@ -1406,7 +1506,7 @@ inline size_t bisect_queue_entries(int64_t cnt) { return (size_t)cnt * 24 + 8192
 // relative bound used by the certificates of the accelerated bisection: 2.01 x ((terms per thread) + 8 reduction levels +
 // reciprocal (<= 1.6 ulp) + slack) x 2^-53; 0 = not available (N > 2^21: the bound would no longer be small)
 inline double bisect_th2(const Problem &P) {
-    if (P.N > ((int64_t)1 << 21) || !(P.dbound > 0.0)) return 0.0;
+    if (P.N > ((int64_t)1 << 21)) return 0.0;
     const double terms = (double)(P.Np / BTL) * BE;
     return 2.01 * (terms + 16.0) * 1.1102230246251565e-16;
 }
@@ -1430,7 +1530,7 @@ inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O
         // and nothing ever waits when every eigenpair has a slot of its own from the start
         quantum = (cnt <= (int64_t)grid * nslot) ? 0 : (int)std::min<int64_t>(32, std::max<int64_t>(8, 128 / std::max<int64_t>(1, ntiles)));
     }
-    const double th2 = (round == 0 && accel && kx) ? bisect_th2(P) : 0.0;
+    const double th2 = (accel && (kx || round == 1)) ? bisect_th2(P) : 0.0;
 #define AH_LAUNCH_BISECT(KD, RD, NS, AC) k_bisect<KD, RD, NS, AC><<<grid, BT, smem, st>>>(P, O, ks, kbase, cnt, dlist, rlist, dcount, queue, qcap, tag, quantum, window, spec, kx, th2)
 #define AH_LAUNCH_KIND(RD, NS, AC)                                          \
     switch (kind) {                                                         \
@@ -1438,8 +1538,10 @@ inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O
         case KIND_DPR1: AH_LAUNCH_BISECT(KIND_DPR1, RD, NS, AC); break;     \
         default: AH_LAUNCH_BISECT(KIND_HALF, RD, NS, AC); break;            \
     }
-    if (round == 1) { AH_LAUNCH_KIND(1, 8, 0) }
-    else if (th2 > 0.0) {
+    if (round == 1) {
+        if (th2 > 0.0) { AH_LAUNCH_KIND(1, 8, 1) }
+        else { AH_LAUNCH_KIND(1, 8, 0) }
+    } else if (th2 > 0.0) {
         if (nslot == 8) { AH_LAUNCH_KIND(0, 8, 1) }
         else if (nslot == 7) { AH_LAUNCH_KIND(0, 7, 1) }
         else { AH_LAUNCH_KIND(0, 6, 1) }
@@ -1452,12 +1554,13 @@ inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O
     return (int)cudaGetLastError();
 }
 inline int launch_rem3_prep(int kind, const Problem &P, const Outputs &O, KState *ks, int64_t kbase, int64_t cnt, int64_t *rlist,
-                            int64_t *dlist, unsigned long long *dcount, int sm_count, cudaStream_t st) {
+                            int64_t *dlist, unsigned long long *dcount, int sm_count, cudaStream_t st, int accel = 0) {
     const int grid = (int)std::min<int64_t>(cnt, (int64_t)sm_count * 4);
+    const double th2 = accel ? bisect_th2(P) : 0.0;
     switch (kind) {
-        case KIND_ARROW: k_rem3_prep<KIND_ARROW><<<grid, RT, 0, st>>>(P, O, ks, kbase, rlist, dlist, dcount); break;
-        case KIND_DPR1: k_rem3_prep<KIND_DPR1><<<grid, RT, 0, st>>>(P, O, ks, kbase, rlist, dlist, dcount); break;
-        default: k_rem3_prep<KIND_HALF><<<grid, RT, 0, st>>>(P, O, ks, kbase, rlist, dlist, dcount); break;
+        case KIND_ARROW: k_rem3_prep<KIND_ARROW><<<grid, RT, 0, st>>>(P, O, ks, kbase, rlist, dlist, dcount, th2); break;
+        case KIND_DPR1: k_rem3_prep<KIND_DPR1><<<grid, RT, 0, st>>>(P, O, ks, kbase, rlist, dlist, dcount, th2); break;
+        default: k_rem3_prep<KIND_HALF><<<grid, RT, 0, st>>>(P, O, ks, kbase, rlist, dlist, dcount, th2); break;
     }
     return (int)cudaGetLastError();
 }

@@ -554,7 +554,7 @@ def test_time_slicing_is_bitwise_schedule_independent(kind, monkeypatch):
         finally:
             ctx.close()
     ref = outs[0]
-    assert ref[1].sum() > 40 * n              # real bisections happened
+    assert ref[1].sum() > 10 * n              # real bisections happened (~18 sweeps per eigenpair with the certified skipping)
     for o in outs[1:]:
         for a_, b_ in zip(ref[:5], o[:5]):
             assert np.array_equal(a_, b_, equal_nan=True)
