@@ -344,6 +344,7 @@ struct BSlot {   // cold per-slot state, touched by warp j only
     double knu0, krho, sig2;   // round 1: first K_nu (HalfArrow keeps it), K_rho, squared shift (HalfArrow)
     // accelerated bisection (ACCEL): the point the coming sweep evaluates (the grid midpoint m or a probe), certified bounds, history
     double x, lo, hi, hx1, hF1, hx2, hF2, pole;
+    double hx0, hF0, Flo, Fhi;   // third point of the history; F at the certified bounds (regula falsi fallback of the probe model)
     int nhist, probing, nprobe, nfail, cert;
 };
 struct BisectShared {
@@ -499,6 +500,7 @@ __device__ __forceinline__ int accel_certifiable(const Problem &P, const BSlot &
 __device__ __forceinline__ void accel_reset(BSlot &S, int cert) {
     S.cert = cert;
     S.lo = -INFINITY; S.hi = INFINITY; S.hx1 = 0.0; S.hF1 = 0.0; S.hx2 = 0.0; S.hF2 = 0.0;
+    S.hx0 = 0.0; S.hF0 = 0.0; S.Flo = INFINITY; S.Fhi = -INFINITY;
     S.pole = S.sideR ? S.left : S.right;
     S.nhist = 0; S.probing = cert; S.nprobe = 0; S.nfail = 0;
     S.x = S.m;
@@ -512,13 +514,15 @@ __device__ __forceinline__ void accel_update(BSlot &S, double sum, double th2) {
     const double F = dec(sum);
     if (S.cert && fabs(sum) > 1.0e-250 && fabs(sum) <= 1.7976931348623157e308) {
         const bool la = dec(__dmul_rn(sum, 1.0 + th2)) > 0.0, lb = dec(__dmul_rn(sum, 1.0 - th2)) > 0.0;
-        if (la && lb) S.lo = fmax(S.lo, x);
-        else if (!la && !lb) S.hi = fmin(S.hi, x);
-        else if (!grid && ++S.nfail >= 2) S.probing = 0;
+        if (la && lb) { if (x > S.lo) { S.lo = x; S.Flo = F; } }
+        else if (!la && !lb) { if (x < S.hi) { S.hi = x; S.Fhi = F; } }
+        else if (!grid && ++S.nfail >= 3) S.probing = 0;    // (every failed probe widens the next probe's offset 4x)
     }
     if (fabs(F) <= 1.7976931348623157e308) {
-        S.hx1 = S.hx2; S.hF1 = S.hF2; S.hx2 = x; S.hF2 = F;
-        if (S.nhist < 2) S.nhist += 1;
+        if (S.nhist == 0 || x != S.hx2) {
+            S.hx0 = S.hx1; S.hF0 = S.hF1; S.hx1 = S.hx2; S.hF1 = S.hF2; S.hx2 = x; S.hF2 = F;
+            if (S.nhist < 3) S.nhist += 1;
+        }
     } else {
         S.probing = 0;
     }
@@ -537,10 +541,12 @@ __device__ __forceinline__ void accel_descend(BSlot &S) {
     }
     S.left = l; S.right = r; S.m = m;
 }
-// Where the coming sweep evaluates F: the grid midpoint, or a probe that tightens lo / hi.  Model through the last two
-// evaluated points: value(m) = L(m) + alpha + gamma / (m - pole), L(m) = b - m in round 0 (the known linear part of the arrow's
-// secular function), 0 in round 1; the probe sits delta = 2 x (certifiable distance) to the side of the model's root whose
-// certificate is further away.  Heuristic only: no influence on the result.
+// Where the coming sweep evaluates F: the grid midpoint, or a probe that tightens lo / hi.  Root estimate from the model
+// value(m) = L(m) + alpha + gamma / (m - q) through the last evaluated points, L(m) = b - m in round 0 (the known linear part
+// of the arrow's secular function), 0 in round 1: with three points q is fitted too (it lumps the poles behind the extreme
+// one), with two q = the extreme pole; if neither lands inside the certified interval, regula falsi on its ends.  The probe
+// sits delta = 1.5 x (certifiable distance) -- 4x more after every probe that could not be certified, never below 4 ulp -- to
+// the side of the estimate whose certificate is further away.  Heuristic only: no influence on the result.
 template <int ROUND>
 __device__ __forceinline__ void accel_choose(BSlot &S, double th2) {
     double x = S.m;
@@ -551,20 +557,31 @@ __device__ __forceinline__ void accel_choose(BSlot &S, double th2) {
         const double L1 = (ROUND == 0) ? S.b - x1 : 0.0, L2 = (ROUND == 0) ? S.b - x2 : 0.0;
         const double R1 = F1 - L1, R2 = F2 - L2;
         const double scale = (ROUND == 0) ? fabs(L2) + fabs(R2) : 1.0 + fabs(sign_jl(S.b) * F2 + 1.0);   // magnitude of the operands of the last addition
-        const double delta = 2.0 * th2 * scale * rcp_fast(slope);
+        double delta = 1.5 * th2 * scale * rcp_fast(slope) * (double)(1 << (2 * S.nfail));
+        delta = fmax(delta, 4.0 * kEps * fabs(x2));
         if (!((b_ - a_) > 6.0 * delta)) S.probing = 0;          // (also when delta is NaN)
         else {
-            const double i1 = rcp_fast(x1 - p), i2 = rcp_fast(x2 - p);
-            const double gam = (R1 - R2) * rcp_fast(i1 - i2), alpha = R2 - gam * i2;
-            double xs;
-            if (ROUND == 0) {   // (b + alpha - m)(m - p) + gamma = 0
-                const double B = S.b + alpha + p, C = (S.b + alpha) * p - gam;
-                const double sq = sqrt(B * B - 4.0 * C);
-                const double ra = (B + sq) / 2.0, rb = (B - sq) / 2.0;
-                xs = (ra > a_ && ra < b_) ? ra : rb;
-            } else {
-                xs = p - gam * rcp_fast(alpha);
+            auto root_with_pole = [&](double q) {
+                const double i1 = rcp_fast(x1 - q), i2 = rcp_fast(x2 - q);
+                const double gam = (R1 - R2) * rcp_fast(i1 - i2), alpha = R2 - gam * i2;
+                if (ROUND == 0) {   // (b + alpha - m)(m - q) + gamma = 0
+                    const double B = S.b + alpha + q, C = (S.b + alpha) * q - gam;
+                    const double sq = sqrt(B * B - 4.0 * C);
+                    const double ra = (B + sq) / 2.0, rb = (B - sq) / 2.0;
+                    return (ra > a_ && ra < b_) ? ra : rb;
+                }
+                return q - gam * rcp_fast(alpha);
+            };
+            double xs = NAN;
+            if (S.nhist >= 3) {
+                const double x0 = S.hx0, R0 = S.hF0 - ((ROUND == 0) ? S.b - x0 : 0.0);
+                const double rho = (R0 - R1) * (x2 - x1) * rcp_fast((R1 - R2) * (x1 - x0));
+                const double qq = (x2 - rho * x0) * rcp_fast(1.0 - rho);
+                const double off = S.sideR ? qq - p : p - qq;      // the fitted pole must not lie on the root's side of the extreme pole
+                if (off <= 0.0) xs = root_with_pole(qq);
             }
+            if (!(xs > a_ && xs < b_)) xs = root_with_pole(p);
+            if (!(xs > a_ && xs < b_) && S.lo >= S.left && S.hi <= S.right) xs = S.lo + (S.hi - S.lo) * S.Flo * rcp_fast(S.Flo - S.Fhi);
             const double xp = ((xs - a_) > (b_ - xs)) ? xs - delta : xs + delta;
             if (xp > a_ && xp < b_) { x = xp; S.nprobe += 1; }
         }
@@ -866,6 +883,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                                 KExtra &X = kx[S.k - kbase];
                                 X.lo = S.lo; X.hi = S.hi; X.hx1 = S.hx1; X.hF1 = S.hF1; X.hx2 = S.hx2; X.hF2 = S.hF2; X.pole = S.pole;
                                 X.nhist = (int8_t)S.nhist; X.probing = (int8_t)S.probing; X.nprobe = (int8_t)S.nprobe; X.nfail = (int8_t)S.nfail;
+                                G.nu = S.hx0; G.mu = S.hF0; G.lambda = S.Flo; G.knu = S.Fhi;   // (free until the finalize)
                             }
                             __threadfence();
                             const unsigned long long r = atomicAdd(dcount + 4, 1ull);
@@ -939,6 +957,7 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                             const int pk = __ldcg(reinterpret_cast<const int *>(&X.nhist));
                             S.nhist = (int)(int8_t)(pk & 0xff); S.probing = (int)(int8_t)((pk >> 8) & 0xff);
                             S.nprobe = (int)(int8_t)((pk >> 16) & 0xff); S.nfail = (int)(int8_t)((pk >> 24) & 0xff);
+                            S.hx0 = __ldcg(&G.nu); S.hF0 = __ldcg(&G.mu); S.Flo = __ldcg(&G.lambda); S.Fhi = __ldcg(&G.knu);
                         }
                     }
                 }
@@ -973,18 +992,23 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
 #pragma unroll
             for (int j = 0; j < NSLOT; ++j) { const int aj = sh.act[j]; if (aj == 1) busy |= 1u << j; else if (aj != 3) idle |= 1u << j; }
             const int nb = __popc(busy), ni = __popc(idle);
-            const int h = (nb == 0) ? 0 : (ni >= 6 * nb ? 6 : (ni >= 2 * nb ? 2 : 0));
-            if (h) {                                                    // CTA-uniform
+            // two helpers for as many leaders as the idle slots allow, four more for the first of them where they last
+            const int nb2 = min(nb, ni >> 1), nb6 = min(nb2, (ni - 2 * nb2) >> 2);
+            if (nb2) {                                                  // CTA-uniform
                 if (warp < NSLOT && lane == 0) {
                     auto nth_bit = [](unsigned mask, int r) { for (int q = 0; q < r; ++q) mask &= mask - 1; return __ffs(mask) - 1; };
                     if ((busy >> warp) & 1u) {                          // leader: its helpers, in ascending slot order
                         const int rank = __popc(busy & ((1u << warp) - 1u));
-                        for (int t = 0; t < h; ++t) sh.grp[warp][t] = nth_bit(idle, rank * h + t);
+                        const int h = rank < nb6 ? 6 : (rank < nb2 ? 2 : 0);
+                        const int off = rank < nb6 ? 6 * rank : 6 * nb6 + 2 * (rank - nb6);
+                        for (int t = 0; t < h; ++t) sh.grp[warp][t] = nth_bit(idle, off + t);
                         sh.grpn[warp] = h;
                     } else {
                         const int ri = __popc(idle & ((1u << warp) - 1u));
-                        if (((idle >> warp) & 1u) && ri < nb * h) {     // helper number t of leader L
-                            const int L = nth_bit(busy, ri / h), t = ri % h;
+                        if (((idle >> warp) & 1u) && ri < 6 * nb6 + 2 * (nb2 - nb6)) {     // helper number t of leader L
+                            const int lr = ri < 6 * nb6 ? ri / 6 : nb6 + (ri - 6 * nb6) / 2;
+                            const int t = ri < 6 * nb6 ? ri % 6 : (ri - 6 * nb6) % 2;
+                            const int L = nth_bit(busy, lr);
                             const BSlot &Ls = sh.slot[L];
                             const double l = Ls.left, r = Ls.right, m = Ls.m;
                             const double mA = (l + m) / 2.0, mB = (m + r) / 2.0;

@@ -289,7 +289,8 @@ def roofline_of(P, res, acc, steps, cnt, fp64, peaks, world):
         "frac": achieved_tf / peak_tf, "traffic": traffic,
         "peak_source": {"fp64_tflops": peak_tf, "measured": fp64, "ncu_sm__inst_executed_pipe_fp64_per_launch": ncu_pipe,
                         "ncu_file": "profiles/r2_*_full_*.md (same build; per-launch FP64-pipe instruction count = 7 x terms / 32 lanes + boundary code)"},
-        "how": "FP64-pipe lane-instructions x2 (FMA-equivalent); 7 per secular term x steps_k x N terms per eigenpair / device time of "
+        "how": "EXECUTED FP64-pipe lane-instructions x2 (FMA-equivalent); 7 per secular term x sweeps_k x N terms per eigenpair (sweeps_k = the O(N) "
+               "evaluations of the secular function k_bisect really ran, res.steps) / device time of "
                "k_bisect (round 0 + the Remedy-3 round, CUDA events on their streams inside the timed region); peak = DFMA burst measured "
                "live in this run (peak_source.measured)",
         "terms_per_launch": terms, "kernel_ms": t_main * 1e3, "fast_eigenpairs": int(res.stats["n_fast"]),
@@ -423,6 +424,30 @@ def _run_ours(args):
     except Exception:
         pass
     roofline = roofline_of(P, res, acc, args.steps, cnt, fp64, peaks, world)
+    # What the reference's algorithm would have executed: plain bisection (ARROWHEAD_B200_ACCEL=0) takes ~54 sweeps per
+    # eigenpair where the certified skipping of k_bisect evaluates ~16 -- same final brackets, bit for bit.  One untimed
+    # solve with the knob off counts them; `roofline.frac` stays the EXECUTED work over the FP64 peak.
+    try:
+        os.environ["ARROWHEAD_B200_ACCEL"] = "0"
+        ctx_plain = ab.Context(local_rank)
+        os.environ.pop("ARROWHEAD_B200_ACCEL", None)
+        rp = P.solve(ctx_plain, k0, k1, Uptr, Vptr)
+        torch.cuda.synchronize()
+        fastp = (rp.status & 0xff) == 0
+        plain_terms = float(rp.steps[fastp].astype(np.float64).sum()) * P.npoles
+        same = bool(np.array_equal(rp.lam, res.lam, equal_nan=True) and np.array_equal(rp.status, res.status))
+        t_main = roofline["kernel_ms"] * 1e-3
+        roofline["reference_algorithm"] = {
+            "terms_per_launch": plain_terms, "sweeps_per_eigenpair": float(rp.steps.mean()), "executed_sweeps_per_eigenpair": float(res.steps.mean()),
+            "equivalent_tflops": 2.0 * FP64_INSTR_PER_TERM * plain_terms / t_main / 1e12,
+            "equivalent_frac": 2.0 * FP64_INSTR_PER_TERM * plain_terms / t_main / 1e12 / roofline["peak"],
+            "plain_bisection_kernel_ms": float(rp.stats["main_kernel_ms"]), "bitwise_identical_lambda_and_status": same,
+            "what": "secular terms of the reference's plain bisection on the same input (one untimed solve with ARROWHEAD_B200_ACCEL=0) over "
+                    "the accelerated kernel's time: > 1 means the certified skipping does more than the FP64 pipe could by brute force"}
+        ctx_plain.close()
+    except Exception as e:
+        os.environ.pop("ARROWHEAD_B200_ACCEL", None)
+        roofline["reference_algorithm"] = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     # ---- end to end: host D,z in, eigenvalues + Info + this rank's eigenvectors out to pinned host memory
     e2e = None
