@@ -85,7 +85,10 @@ typedef struct ah_result {
     double  *knu;        /* [cnt] host */
     double  *krho;       /* [cnt] host */
     int64_t *qout;       /* [cnt] host */
-    int32_t *steps;      /* [cnt] bisection steps taken for this eigenpair (not in the reference; for roofline accounting) */
+    int32_t *steps;      /* [cnt] O(N) sweeps (evaluations of the secular function) spent on this eigenpair -- not in the reference;
+                          * for roofline accounting.  Plain bisection takes ~54; the library decides most of those steps from
+                          * certified bounds and evaluates ~15, with the same final bracket bit for bit (DESIGN.md section 3;
+                          * environment ARROWHEAD_B200_ACCEL=0 at ah_create selects plain bisection) */
     int32_t *status;     /* [cnt] AH_ST_* bits, host */
     /* Eigenvectors.  Column c of U starts at U + c*ldu.  Entry r of the vector goes to row
      * rowmap[r] (0-based) when rowmap != NULL (the deflation case `U[zx,zx[k]] = v`,
@@ -110,7 +113,7 @@ typedef struct ah_stats {
     int64_t launches;         /* number of kernels launched by the call */
     int64_t n_fast;           /* eigenpairs finished by the fast-path kernels (k_prep -> k_bisect -> k_vec) */
     int64_t n_full;           /* eigenpairs routed to the full (Remedy / double-double) kernel */
-    int64_t total_steps;      /* sum of bisection steps */
+    int64_t total_steps;      /* sum of `steps` (sweeps evaluated) */
     int64_t h2d_bytes, d2h_bytes;
     double  prep_ms, bisect_ms, vec_ms, full_ms;   /* per-kernel device time: k_prep, k_bisect (+ Remedy-3 round), k_vec, k_full */
     int64_t n_rem3;           /* eigenpairs that took the Remedy-3 round of the fast path (counted in n_fast) */
