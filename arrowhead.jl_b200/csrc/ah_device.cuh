@@ -166,6 +166,15 @@ __device__ __forceinline__ double secular_term_acc(double acc, double d, double 
     return __fma_rn(w2, rcp_fast(t), acc);
 }
 
+// First term of a tile sum: the fast kernels add the terms of one tile (4 poles per thread) among themselves first and the
+// tile sums to the running sum afterwards -- 4 + (tiles per sweep) roundings per accumulator instead of 4 x tiles, which is
+// what makes the error bound of the bisection certificates (ah_pipe.cuh) three times tighter at n = 32768.
+__device__ __forceinline__ double secular_term_first(double d, double m, double w2) {
+    double e = __fma_rn(-m, d, 1.0);
+    double t = __dmul_rn(d, e);
+    return __dmul_rn(w2, rcp_fast(t));
+}
+
 // The same term with IEEE divisions only: w2/(d*(1-m*d)) is +-Inf when the bisection point sits exactly on an inverse
 // pole (as z'^2/(D'-m) is in the reference) and 0 when the denominator overflows, where the reciprocal-seed version
 // above produces NaN (0*Inf inside the correction).  Used to redo a sweep whose sum came out NaN.

@@ -1098,9 +1098,11 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                 // (The same test costs the full-occupancy loop 2-4 %: measured.)
                 if (ROUND == 0 || ((actmask >> j) & 1u)) {
                     const double2 h = sh.hot[j];   // (sigma_j, m_j): broadcast LDS.128, reloaded per tile to save 32 registers
+                    double t = secular_term_first(dshift<KIND>(Dv[0], h.x), h.y, W2[0]);    // tile sum first, then the running sum
 #pragma unroll
-                    for (int e = 0; e < BE; ++e)
-                        acc[j] = secular_term_acc(acc[j], dshift<KIND>(Dv[e], h.x), h.y, W2[e]);
+                    for (int e = 1; e < BE; ++e)
+                        t = secular_term_acc(t, dshift<KIND>(Dv[e], h.x), h.y, W2[e]);
+                    acc[j] = __dadd_rn(acc[j], t);
                 }
             }
 
@@ -1111,13 +1113,17 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
                     if ((fixmask >> j) & 1u) {
                         const int sk = sh.skip[j];
                         if (sk / BTL == tile) {
-                            double a = sh.save[j];
                             const double2 h = sh.hot[j];
+                            double t = 0.0;                    // the tile sum without the pole: its other three terms in order
+                            bool have = false;
 #pragma unroll
                             for (int e = 0; e < BE; ++e)
-                                if (base + elem_offset(tid, e) != sk)
-                                    a = secular_term_acc(a, dshift<KIND>(Dv[e], h.x), h.y, W2[e]);
-                            acc[j] = a;
+                                if (base + elem_offset(tid, e) != sk) {
+                                    t = have ? secular_term_acc(t, dshift<KIND>(Dv[e], h.x), h.y, W2[e])
+                                             : secular_term_first(dshift<KIND>(Dv[e], h.x), h.y, W2[e]);
+                                    have = true;
+                                }
+                            acc[j] = __dadd_rn(sh.save[j], t);
                         }
                     }
                 }
@@ -1265,10 +1271,12 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
                     for (int u = 0; u < RU; ++u) {
                         if (tile0 + u < ntiles) {
 #pragma unroll
-                            for (int h = 0; h < RH; ++h) {
-                                acc = secular_term_acc(acc, dshift<KIND>(dcur[u][h].x, S.sigma), S.x, wcur[u][h].x);
-                                acc = secular_term_acc(acc, dshift<KIND>(dcur[u][h].y, S.sigma), S.x, wcur[u][h].y);
-                            }
+                            static_assert(RH == 2, "tile sum of four terms, as in k_bisect");
+                            double t = secular_term_first(dshift<KIND>(dcur[u][0].x, S.sigma), S.x, wcur[u][0].x);
+                            t = secular_term_acc(t, dshift<KIND>(dcur[u][0].y, S.sigma), S.x, wcur[u][0].y);
+                            t = secular_term_acc(t, dshift<KIND>(dcur[u][1].x, S.sigma), S.x, wcur[u][1].x);
+                            t = secular_term_acc(t, dshift<KIND>(dcur[u][1].y, S.sigma), S.x, wcur[u][1].y);
+                            acc = __dadd_rn(acc, t);
                         }
                     }
 #pragma unroll
@@ -1527,12 +1535,14 @@ inline size_t bisect_queue_entries(int64_t cnt) { return (size_t)cnt * 24 + 8192
 
 // quantum: steps an eigenpair keeps its slot while others wait (0: no time slicing, < 0: chosen here);
 // window: time slicing starts when fewer than window x (all slots) eigenpairs are waiting; tag: unique per launch, != 0
-// relative bound used by the certificates of the accelerated bisection: 2.01 x ((terms per thread) + 8 reduction levels +
-// reciprocal (<= 1.6 ulp) + slack) x 2^-53; 0 = not available (N > 2^21: the bound would no longer be small)
+// relative bound used by the certificates of the accelerated bisection: 2.01 x (roundings per accumulator + 8 reduction
+// levels + reciprocal (<= 1.6 ulp) + slack) x 2^-53; 0 = not available (N > 2^21: the bound would no longer be small)
 inline double bisect_th2(const Problem &P) {
     if (P.N > ((int64_t)1 << 21)) return 0.0;
-    const double terms = (double)(P.Np / BTL) * BE;
-    return 2.01 * (terms + 16.0) * 1.1102230246251565e-16;
+    // per accumulator: BE roundings inside a tile sum + one per tile for the running sum; 8 reduction levels; <= 1.6 ulp per
+    // reciprocal; slack
+    const double depth = (double)(P.Np / BTL) + BE;
+    return 2.01 * (depth + 8.0 + 1.6 + 4.4) * 1.1102230246251565e-16;
 }
 inline int launch_bisect(int kind, int round, const Problem &P, const Outputs &O, KState *ks, int64_t kbase, int64_t cnt,
                          int64_t *dlist, int64_t *rlist, unsigned long long *dcount, unsigned long long *queue, long long qcap,

@@ -30,7 +30,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "SymArrow n=%d full eigen(): eigenpairs/s"
-FP64_INSTR_PER_TERM = 7.0     # DADD d, DFMA e, DMUL t, 3 DFMA reciprocal refinement, DFMA accumulate (ah_device.cuh)
+FP64_INSTR_PER_TERM = 7.25    # DADD d, DFMA e, DMUL t, 3 DFMA reciprocal refinement, DFMA/DMUL accumulate + one DADD per tile sum of 4 (ah_device.cuh)
 
 
 def gen_symarrow(n, seed=421):
@@ -289,7 +289,7 @@ def roofline_of(P, res, acc, steps, cnt, fp64, peaks, world):
         "frac": achieved_tf / peak_tf, "traffic": traffic,
         "peak_source": {"fp64_tflops": peak_tf, "measured": fp64, "ncu_sm__inst_executed_pipe_fp64_per_launch": ncu_pipe,
                         "ncu_file": "profiles/r2_*_full_*.md (same build; per-launch FP64-pipe instruction count = 7 x terms / 32 lanes + boundary code)"},
-        "how": "EXECUTED FP64-pipe lane-instructions x2 (FMA-equivalent); 7 per secular term x sweeps_k x N terms per eigenpair (sweeps_k = the O(N) "
+        "how": "EXECUTED FP64-pipe lane-instructions x2 (FMA-equivalent); 7.25 per secular term x sweeps_k x N terms per eigenpair (sweeps_k = the O(N) "
                "evaluations of the secular function k_bisect really ran, res.steps) / device time of "
                "k_bisect (round 0 + the Remedy-3 round, CUDA events on their streams inside the timed region); peak = DFMA burst measured "
                "live in this run (peak_source.measured)",

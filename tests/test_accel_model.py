@@ -174,7 +174,7 @@ def families(n, seed):
 
 
 def th2_of(N):
-    return 2.01 * (4 * ((N + 1023) // 1024) + 16) * 2.0 ** -53          # bisect_th2 (ah_pipe.cuh)
+    return 2.01 * ((N + 1023) // 1024 + 4 + 14) * 2.0 ** -53          # bisect_th2 (ah_pipe.cuh): tile sums of 4, one rounding per tile
 
 
 @pytest.mark.parametrize("n", [300, 2500])
