@@ -97,3 +97,58 @@ def test_accelerated_bisection_at_the_headline_size(monkeypatch):
         assert s1 < 0.5 * s0
     finally:
         plain.close(); fast.close()
+
+
+def _fuzz_problem(rng, N):
+    """a random structured spectrum: uniform / clustered / graded pieces glued together, weights over many decades"""
+    parts, left = [], N
+    while left > 0:
+        m = int(min(left, rng.integers(1, max(2, N // 2))))
+        kind = rng.integers(0, 5)
+        c = rng.normal() * 10.0 ** rng.integers(-3, 4)
+        if kind == 0: p = c + rng.random(m)
+        elif kind == 1: p = c + 10.0 ** rng.integers(-12, -2) * rng.random(m)            # a cluster
+        elif kind == 2: p = c * 2.0 ** (-40 * rng.random(m))                             # graded towards 0
+        elif kind == 3: p = c + np.arange(m) * 10.0 ** rng.integers(-9, 0)               # equispaced
+        else: p = rng.standard_normal(m) * 10.0 ** rng.integers(-6, 7)
+        parts.append(p); left -= m
+    D = np.unique(np.concatenate(parts))[::-1].copy()
+    D = D[np.isfinite(D)]
+    keep = np.concatenate([[True], np.diff(D) < 0])
+    D = D[keep]
+    w = (rng.random(D.size) + 1e-3) * 10.0 ** (rng.integers(-12, 3) * rng.random(D.size))
+    w *= np.where(rng.random(D.size) < 0.5, 1.0, -1.0)
+    return D, w
+
+
+@pytest.mark.timeout(900)
+def test_accelerated_bisection_fuzz(monkeypatch):
+    """random structured inputs, all three matrix types: every output bit equals plain bisection's"""
+    plain, fast = _contexts(monkeypatch)
+    try:
+        rng = np.random.default_rng(20261020)
+        done = 0
+        for case in range(90):
+            N = int(rng.choice([7, 33, 120, 500, 1100, 2300]))
+            D, w = _fuzz_problem(rng, N)
+            if D.size < 3:
+                continue
+            a = float(rng.normal() * 10.0 ** rng.integers(-3, 6))
+            kind = case % 3
+            if kind == 0:
+                _same(plain.symarrow(D, w, a), fast.symarrow(D, w, a), ("fuzz symarrow", case, D.size))
+            elif kind == 1:
+                rho = abs(a) + 1e-3
+                _same(plain.symdpr1(D, w, rho), fast.symdpr1(D, w, rho), ("fuzz symdpr1", case, D.size))
+            else:
+                Dh = np.unique(np.abs(D))[::-1].copy()
+                Dh = Dh[Dh > 0]
+                if Dh.size < 3:
+                    continue
+                tip = case % 2
+                zh = np.resize(w, Dh.size + tip)
+                _same(plain.halfarrow(Dh, zh), fast.halfarrow(Dh, zh), ("fuzz halfarrow", case, Dh.size, tip))
+            done += 1
+        assert done >= 80
+    finally:
+        plain.close(); fast.close()
