@@ -49,7 +49,7 @@ EXPORTS = [
     "ah_symarrow_eigen", "ah_symdpr1_eigen", "ah_halfarrow_svd", "ah_resolve",
     "ah_device_malloc", "ah_device_free", "ah_host_alloc_pinned", "ah_host_free_pinned",
     "ah_memcpy_d2h", "ah_memcpy_h2d", "ah_set_identity", "ah_apply_givens_rows", "ah_gather_permuted",
-    "ah_scale_rows_phase", "ah_symarrow_eigvals_dd", "ah_symarrow_eigen_batched", "ah_gather_elements", "ah_gather_permuted_batched",
+    "ah_scale_rows_phase", "ah_gather_permuted_phase", "ah_symarrow_eigvals_dd", "ah_symarrow_eigen_batched", "ah_gather_elements", "ah_gather_permuted_batched",
     "ah_copy2d_batched", "ah_dgemm_batched",
     "ah_measure_fp64_peak", "ah_measure_term_peak", "ah_measure_rcp_seed_error", "ah_measure_store_bw",
     "ah_set_async", "ah_wait", "ah_last_gemm_ms", "ah_measure_dmma_peak",
@@ -95,6 +95,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ah_set_identity.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64]
     lib.ah_apply_givens_rows.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double]
     lib.ah_gather_permuted.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, _i64p, C.c_int64, _i64p, C.c_int64]
+    lib.ah_gather_permuted_phase.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, _i64p, C.c_int64, _i64p, C.c_int64, _dp, C.c_int]
     u64p = C.POINTER(C.c_uint64)
     lib.ah_symarrow_eigvals_dd.argtypes = [vp, C.c_int64, _dp, _dp, _dp, C.c_double, C.c_double, _dp, C.c_int64, C.c_int64,
                                            C.POINTER(AhResult)]
@@ -349,6 +350,13 @@ class Context:
         rows = np.ascontiguousarray(rows, np.int64); cols = np.ascontiguousarray(cols, np.int64)
         self._check(self.lib.ah_gather_permuted(self.handle, C.c_void_p(int(dst_dev)), ld_dst, C.c_void_p(int(src_dev)),
                                                 ld_src, _ptr(rows, _i64p), rows.size, _ptr(cols, _i64p), cols.size))
+
+    def gather_permuted_phase(self, dst_dev, ld_dst, src_dev, ld_src, rows, cols, phase):
+        rows = np.ascontiguousarray(rows, np.int64); cols = np.ascontiguousarray(cols, np.int64)
+        phase = np.ascontiguousarray(phase, np.float64)
+        self._check(self.lib.ah_gather_permuted_phase(self.handle, C.c_void_p(int(dst_dev)), ld_dst, C.c_void_p(int(src_dev)), ld_src,
+                                                      _ptr(rows, _i64p), rows.size, _ptr(cols, _i64p), cols.size, _ptr(phase, _dp),
+                                                      int(phase.shape[1])))
 
     def scale_rows_phase(self, dst_dev, ld_dst, src_dev, ld_src, phase, nrows, ncols):
         phase = np.ascontiguousarray(phase, np.float64)

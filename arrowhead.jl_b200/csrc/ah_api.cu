@@ -716,6 +716,23 @@ __global__ void k_rcp_seed_error(unsigned long long *out) {
     atomicMax(out, (unsigned long long)__double_as_longlong(worst0));
     atomicMax(out + 1, (unsigned long long)__double_as_longlong(worst1));
 }
+// the arrow driver's final view(U,rows,es) and the Hermitian wrappers' Diagonal(c)*U in ONE pass over the eigenvectors
+template <int NC>
+__global__ void k_gather_phase(double *dst, int64_t ldd, const double *__restrict__ src, int64_t lds, const int64_t *__restrict__ rows,
+                               int64_t nrows, const int64_t *__restrict__ cols, int64_t ncols, const double *__restrict__ phase) {
+    const int64_t total = nrows * ncols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx / nrows, r = idx - c * nrows;
+        const double v = src[cols[c] * lds + rows[r]];
+        double *o = dst + (c * ldd + r) * NC;
+        if (NC == 2) {
+            *reinterpret_cast<double2 *>(o) = make_double2(__dmul_rn(phase[2 * r], v), __dmul_rn(phase[2 * r + 1], v));
+        } else {
+            reinterpret_cast<double2 *>(o)[0] = make_double2(__dmul_rn(phase[4 * r], v), __dmul_rn(phase[4 * r + 1], v));
+            reinterpret_cast<double2 *>(o)[1] = make_double2(__dmul_rn(phase[4 * r + 2], v), __dmul_rn(phase[4 * r + 3], v));
+        }
+    }
+}
 template <int NC>
 __global__ void k_scale_rows_phase(double *dst, int64_t ldd, const double *__restrict__ src, int64_t lds,
                                    const double *__restrict__ phase, int64_t nrows, int64_t ncols) {
@@ -1229,6 +1246,29 @@ int ah_scale_rows_phase(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const doub
     const int grid = ctx->sm_count * 8;
     if (ncomp == 2) k_scale_rows_phase<2><<<grid, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const double *)ctx->dScale.p, nrows, ncols);
     else k_scale_rows_phase<4><<<grid, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const double *)ctx->dScale.p, nrows, ncols);
+    AH_CUDA(cudaGetLastError());
+    return util_done(ctx);
+}
+
+int ah_gather_permuted_phase(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src, const int64_t *rows,
+                             int64_t nrows, const int64_t *cols, int64_t ncols, const double *phase, int ncomp) {
+    if (!ctx || !dst_dev || !src_dev || !rows || !cols || !phase || (ncomp != 2 && ncomp != 4) || nrows < 1 || ncols < 1 || ld_dst < nrows)
+        return AH_ERR_INVALID_ARG;
+    AH_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->dMap1, nrows * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dMap2, ncols * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->dScale, (size_t)nrows * ncomp * 8))) return rc;
+    if ((rc = h2d_staged(ctx, ctx->dMap1.p, rows, nrows * 8))) return rc;
+    if ((rc = h2d_staged(ctx, ctx->dMap2.p, cols, ncols * 8))) return rc;
+    if ((rc = h2d_staged(ctx, ctx->dScale.p, phase, (size_t)nrows * ncomp * 8))) return rc;
+    const int grid = ctx->sm_count * 8;
+    if (ncomp == 2)
+        k_gather_phase<2><<<grid, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const int64_t *)ctx->dMap1.p, nrows,
+                                                          (const int64_t *)ctx->dMap2.p, ncols, (const double *)ctx->dScale.p);
+    else
+        k_gather_phase<4><<<grid, 256, 0, ctx->stream>>>(dst_dev, ld_dst, src_dev, ld_src, (const int64_t *)ctx->dMap1.p, nrows,
+                                                          (const int64_t *)ctx->dMap2.p, ncols, (const double *)ctx->dScale.p);
     AH_CUDA(cudaGetLastError());
     return util_done(ctx);
 }

@@ -89,10 +89,21 @@ def givens(f: float, g: float, i1: int, i2: int):
     return i1, i2, c, s, r
 
 
-def _finish(ctx, Udev, rows, cols, vectors):
-    """Apply the lazy `view(U,rows,cols)` of the reference and hand the vectors out."""
+def _finish(ctx, Udev, rows, cols, vectors, phase=None):
+    """Apply the lazy `view(U,rows,cols)` of the reference and hand the vectors out.  phase (nrows x 2|4): the Hermitian
+    wrappers' `Diagonal(c)*U` (hermitian.jl:107-115) fused into the same pass -- complex / quaternion entries are written once."""
     if Udev is None:
         return None
+    if phase is not None:
+        ncomp = phase.shape[1]
+        out = DeviceMatrix(ctx, rows.size * ncomp, cols.size)
+        ctx.gather_permuted_phase(out.ptr, rows.size, Udev.ptr, Udev.ld, rows, cols, phase)
+        Udev.free()
+        if vectors == "device":
+            return out
+        host = _hyper_to_host(out.to_host(), rows.size, ncomp)
+        out.free()
+        return host
     if not (_is_identity(rows) and _is_identity(cols) and rows.size == Udev.nrows and cols.size == Udev.ncols):
         out = DeviceMatrix(ctx, rows.size, cols.size)
         ctx.gather_permuted(out.ptr, out.ld, Udev.ptr, Udev.ld, rows, cols)
@@ -125,7 +136,7 @@ def _deflate_duplicates(Ds, zs, zx, lam, rotation):
 
 # ---------------------------------------------------------------------------------------------------
 def eigen_symarrow(A: SymArrow, tau=None, *, ctx: Context | None = None, vectors="host", forward_tau=False,
-                   rotation="reference", out: np.ndarray | None = None):
+                   rotation="reference", out: np.ndarray | None = None, phase: np.ndarray | None = None):
     """eigen(A::SymArrow, tau) -> (Eigen(values, vectors), Info).  vectors: "host" | "device" | None.
     out: optional caller-owned Fortran-ordered n x n float64 array for the eigenvectors (pinned memory makes the
     copy PCIe-fast: `Context.pinned_alloc`, torch `pin_memory`); when the input needs no deflation and no
@@ -183,7 +194,7 @@ def eigen_symarrow(A: SymArrow, tau=None, *, ctx: Context | None = None, vectors
     isi = np.argsort(is_, kind="stable")
     es = jl_sortperm_desc(lam)
     rows = np.concatenate([isi[: A.i - 1], [n0 - 1], isi[A.i - 1:]]).astype(np.int64)
-    Uout = _finish(ctx, Udev, rows, es, vectors)
+    Uout = _finish(ctx, Udev, rows, es, vectors, phase)
     if out is not None and isinstance(Uout, np.ndarray):
         out[...] = Uout
         Uout = out
@@ -194,7 +205,7 @@ def eigen_symarrow(A: SymArrow, tau=None, *, ctx: Context | None = None, vectors
 
 
 def eigen_symdpr1(A: SymDPR1, tau=None, *, ctx: Context | None = None, vectors="host", forward_tau=False,
-                  rotation="reference"):
+                  rotation="reference", phase: np.ndarray | None = None):
     """eigen(A::SymDPR1, tau) -> (Eigen, Info)."""
     ctx = ctx or get_context()
     D, u, r = A.D, A.u, A.r
@@ -251,7 +262,7 @@ def eigen_symdpr1(A: SymDPR1, tau=None, *, ctx: Context | None = None, vectors="
     isi = np.argsort(is_, kind="stable")
     lam = signr * lam
     es = jl_sortperm_desc(lam)
-    E = Eigen(lam[es], _finish(ctx, Udev, isi.astype(np.int64), es, vectors))
+    E = Eigen(lam[es], _finish(ctx, Udev, isi.astype(np.int64), es, vectors, phase))
     out_info = info.permuted(es)
     out_info.stats = res.stats if res is not None else None
     return E, out_info
@@ -397,18 +408,25 @@ def eigen_hermarrow(A: HermArrow, tau=None, *, ctx: Context | None = None, vecto
     """eigen(A::HermArrow) (hermitian.jl:107-115) -> (Eigen(values, complex|quaternion vectors), Info)."""
     ctx = ctx or get_context()
     c, zr = phase_split(A.zc)
-    E, info = eigen_symarrow(SymArrow(A.D, zr, A.a, A.i), tau, ctx=ctx, vectors=None if vectors is None else "device", **kw)
     one = np.zeros((1, A.ncomp)); one[0, 0] = 1.0
     phase = np.concatenate([c[: A.i - 1], one, c[A.i - 1:]])          # insert!(c, A.i, one(T))
-    return Eigen(E.values, _apply_phase(ctx, E.vectors, phase, vectors)), info
+    # the phase multiplication rides on the driver's final permutation pass (ah_gather_permuted_phase): no extra pass over U
+    E, info = eigen_symarrow(SymArrow(A.D, zr, A.a, A.i), tau, ctx=ctx, vectors=vectors, phase=phase, **kw)
+    V = E.vectors
+    if isinstance(V, np.ndarray) and not np.iscomplexobj(V) and V.ndim == 2:      # trivial cases answered on the host (1x1, diagonal)
+        V = _apply_phase(ctx, V, phase, vectors)
+    return Eigen(E.values, V), info
 
 
 def eigen_hermdpr1(A: HermDPR1, tau=None, *, ctx: Context | None = None, vectors="host", **kw):
     """eigen(A::HermDPR1) (hermitian.jl:131-139)."""
     ctx = ctx or get_context()
     c, ur = phase_split(A.uc)
-    E, info = eigen_symdpr1(SymDPR1(A.D, ur, A.r), tau, ctx=ctx, vectors=None if vectors is None else "device", **kw)
-    return Eigen(E.values, _apply_phase(ctx, E.vectors, c, vectors)), info
+    E, info = eigen_symdpr1(SymDPR1(A.D, ur, A.r), tau, ctx=ctx, vectors=vectors, phase=c, **kw)
+    V = E.vectors
+    if isinstance(V, np.ndarray) and not np.iscomplexobj(V) and V.ndim == 2:
+        V = _apply_phase(ctx, V, c, vectors)
+    return Eigen(E.values, V), info
 
 
 def eigen(A, tau=None, **kw):

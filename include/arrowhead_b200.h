@@ -251,6 +251,11 @@ int ah_dgemm_batched(ah_ctx *ctx, int64_t nb, int64_t m, int64_t n, int64_t k, c
  * (interleaved components = ComplexF64 / QuaternionF64 layout), phase a host array. */
 int ah_scale_rows_phase(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src,
                         const double *phase, int ncomp, int64_t nrows, int64_t ncols);
+/* The same fused with the driver's final permutation `view(U,rows,es)` (arrowhead3.jl:648-654), so that the Hermitian
+ * wrappers cost no extra pass over the eigenvectors:
+ * dst[(c*ld_dst + r)*ncomp + q] = phase[r*ncomp + q] * src[cols[c]*ld_src + rows[r]]  (rows, cols: 0-based host index vectors). */
+int ah_gather_permuted_phase(ah_ctx *ctx, double *dst_dev, int64_t ld_dst, const double *src_dev, int64_t ld_src, const int64_t *rows,
+                             int64_t nrows, const int64_t *cols, int64_t ncols, const double *phase, int ncomp);
 
 /* The device utilities above (set_identity, apply_givens_rows, gather_permuted[_batched], copy2d_batched,
  * dgemm_batched, scale_rows_phase) synchronise the stream before they return.  ah_set_async(ctx, 1) turns them into
