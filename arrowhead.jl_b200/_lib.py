@@ -217,8 +217,15 @@ class Context:
         # `into`: a RangeResult of the same k-range to fill again (callers that solve repeatedly avoid fresh pages for
         # the nine per-k arrays: at n = 32768 first-touch page faults cost 0.2 ms per call)
         res = into if (into is not None and into.k0 == k0 and into.k1 == k1) else RangeResult(k0, k1)
-        r = AhResult()
-        res.fill(r)
+        r = getattr(res, "_ah", None)            # a reused RangeResult keeps its filled-in struct (the nine numpy -> ctypes pointer
+        if r is None:                            # conversions cost ~30 us of Python per call, 1 % of a 1/8-shard step)
+            r = AhResult()
+            res.fill(r)
+            if res is into:
+                res._ah = r
+        else:                                    # everything but the nine per-k pointers is set afresh below
+            r.U = None; r.ldu = 0; r.U_mem = 0; r.V = None; r.ldv = 0; r.V_mem = 0
+            r.rowmap_u = None; r.rowmap_v = None; r.rowscale_v = None
         cnt = k1 - k0 + 1
         keep = []
         if U_dev is not None:
