@@ -52,7 +52,7 @@ struct ah_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;   // high priority: the short Remedy-3 round runs beside k_vec
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    std::vector<cudaEvent_t> side_ev;     // 2 timing events per column block on the side stream
+    std::vector<cudaEvent_t> side_ev;     // 4 timing events per column block on the side stream (Remedy-3 round, k_full)
     cudaStream_t stream = nullptr;  // the stream kernels run on (own_stream or caller's)
     cudaEvent_t ev[12] = {};
     cudaEvent_t ev_stage[2] = {};
@@ -409,11 +409,15 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         AH_CUDA(cudaEventCreate(&e));
         ctx->chunk_ev.push_back(e);
     }
-    while ((int)ctx->side_ev.size() < 2 * nchunks) {
+    while ((int)ctx->side_ev.size() < 4 * nchunks) {
         cudaEvent_t e;
         AH_CUDA(cudaEventCreate(&e));
         ctx->side_ev.push_back(e);
     }
+    // Single-block calls with eigenvectors: the per-k results leave on the side stream as soon as the Remedy-3 round and
+    // k_full are through, and the caller's arrays are filled from them while the main k_vec is still writing U.
+    if ((rc = ensure_pinned(ctx, out_bytes(cnt)))) return rc;
+    const bool early_perk = ctx->mode == 0 && nchunks == 1 && (wantU || wantV);
     ctx->stats.host_pre_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     for (int64_t c0 = 0, cc = 0; c0 < cnt; c0 += cc, ++nbuf) {
         cc = std::min(nbuf == 0 ? first : chunk, cnt - c0);
@@ -438,6 +442,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         int64_t *dlist = (int64_t *)ctx->dList.p;
         unsigned long long *dcount = (unsigned long long *)ctx->dCount.p;
         AH_CUDA(cudaEventRecord(E[0], st));
+        bool side_full = false;      // k_full ran on the side stream (beside the main k_vec)
         if (ctx->mode == 0) {
             KState *ks = (KState *)ctx->dKs.p;
             int64_t *rlist = (int64_t *)ctx->dRList.p;
@@ -467,7 +472,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                 const int64_t guess = std::max<int64_t>(1, std::min<int64_t>(cc, (int64_t)ctx->sm_count * 2 * ah::BJ));   // full grid; idle slots are skipped
                 const bool overlap = wantU || wantV;
                 cudaStream_t rs = overlap ? ctx->side_stream : st;
-                cudaEvent_t *SE = &ctx->side_ev[2 * (size_t)nbuf];
+                cudaEvent_t *SE = &ctx->side_ev[4 * (size_t)nbuf];
                 if (overlap) {
                     AH_CUDA(cudaEventRecord(ctx->ev_fork, st));
                     AH_CUDA(cudaStreamWaitEvent(rs, ctx->ev_fork, 0));
@@ -483,15 +488,38 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                     // the listed eigenpairs get their vectors on the side stream, too (other columns than the main k_vec's)
                     rc = ah::launch_vec(L.kind, P, Oc, ks, kb, guess, rlist, dcount + 2, ctx->sm_count, rs);
                     if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_vec (Remedy-3 list) launch");
+                    // ... and so does everything else that does not depend on the main k_vec: k_full (its own columns) and the
+                    // per-k results on their way to the host, which the caller's arrays are filled from while k_vec still runs
+                    AH_CUDA(cudaEventRecord(SE[2], rs));
+                    {
+                        const int grid = (int)std::min<int64_t>(cc, (int64_t)ctx->sm_count * 4);
+                        switch (L.kind) {
+                            case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, rs>>>(P, Oc, dlist, kb, 0, dcount); break;
+                            case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, rs>>>(P, Oc, dlist, kb, 0, dcount); break;
+                            default: k_full<KIND_HALF, 256><<<grid, 256, 0, rs>>>(P, Oc, dlist, kb, 0, dcount); break;
+                        }
+                        AH_CUDA(cudaGetLastError());
+                        ctx->stats.launches += 1;
+                    }
+                    AH_CUDA(cudaEventRecord(SE[3], rs));
+                    AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (size_t)nbuf], dcount, 8, cudaMemcpyDeviceToHost, rs));
+                    AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (size_t)nbuf + 1], dcount + 2, 8, cudaMemcpyDeviceToHost, rs));
+                    n_count_reads = nbuf + 1;
+                    if (early_perk) {
+                        AH_CUDA(cudaEventRecord(ctx->ev[6], rs));
+                        AH_CUDA(cudaMemcpyAsync(ctx->hPinned, ctx->dOut.p, out_bytes(cnt), cudaMemcpyDeviceToHost, rs));
+                        AH_CUDA(cudaEventRecord(ctx->ev[7], rs));
+                    }
                     AH_CUDA(cudaEventRecord(ctx->ev_join, rs));
                     rc = ah::launch_vec(L.kind, P, Oc, ks, kb, cc, nullptr, nullptr, ctx->sm_count, st);
                     if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_vec launch");
                     AH_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
                     ctx->stats.launches += 2;
                 }
+                side_full = overlap;
             }
             AH_CUDA(cudaEventRecord(E[3], st));
-            {
+            if (!side_full) {
                 // the hand-over list is consumed straight from device memory; a few hundred CTAs cover the
                 // ~1 % of eigenpairs that take a Remedy / double-double branch
                 const int grid = (int)std::min<int64_t>(cc, (int64_t)ctx->sm_count * 4);
@@ -502,10 +530,10 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                 }
                 AH_CUDA(cudaGetLastError());
                 ctx->stats.launches += 1;
+                AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (size_t)nbuf], dcount, 8, cudaMemcpyDeviceToHost, st));
+                AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (size_t)nbuf + 1], dcount + 2, 8, cudaMemcpyDeviceToHost, st));
+                n_count_reads = nbuf + 1;
             }
-            AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (size_t)nbuf], dcount, 8, cudaMemcpyDeviceToHost, st));
-            AH_CUDA(cudaMemcpyAsync(&ctx->hCounts[2 * (size_t)nbuf + 1], dcount + 2, 8, cudaMemcpyDeviceToHost, st));
-            n_count_reads = nbuf + 1;
             AH_CUDA(cudaEventRecord(E[4], st));
         } else {
             AH_CUDA(cudaEventRecord(E[3], st));
@@ -561,35 +589,7 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
     }
 #endif
     // ---- per-k outputs -> host
-    AH_CUDA(cudaEventRecord(ctx->ev[6], st));
-    if ((rc = ensure_pinned(ctx, out_bytes(cnt)))) return rc;
-    AH_CUDA(cudaMemcpyAsync(ctx->hPinned, ctx->dOut.p, out_bytes(cnt), cudaMemcpyDeviceToHost, st));
-    AH_CUDA(cudaEventRecord(ctx->ev[7], st));
-    AH_CUDA(wait_stream(ctx, st));
-    if (staged) AH_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-    const auto t_synced = std::chrono::steady_clock::now();
-    for (int c = 0; c < nchunks; ++c) {   // kernel times of every column block
-        cudaEvent_t *E = &ctx->chunk_ev[5 * (size_t)c];
-        float t = 0.f;
-        AH_CUDA(cudaEventElapsedTime(&t, E[0], E[4]));
-        ms_all += t;
-        AH_CUDA(cudaEventElapsedTime(&t, E[3], E[4]));
-        ctx->stats.full_ms += t;
-        if (ctx->mode == 0) {
-            AH_CUDA(cudaEventElapsedTime(&t, E[0], E[1]));
-            ctx->stats.prep_ms += t;
-            AH_CUDA(cudaEventElapsedTime(&t, E[1], E[2]));
-            ctx->stats.bisect_ms += t;
-            ms_main += t;
-            AH_CUDA(cudaEventElapsedTime(&t, ctx->side_ev[2 * (size_t)c], ctx->side_ev[2 * (size_t)c + 1]));
-            ctx->stats.rem3_ms += t;          // runs beside k_vec: contained in the span below when vectors are wanted
-            ms_main += t;
-            AH_CUDA(cudaEventElapsedTime(&t, E[2], E[3]));
-            ctx->stats.vec_ms += t;
-        }
-    }
-    ctx->stats.d2h_bytes += cnt * (8 * 7 + 4 * 2);
-    {
+    auto unpack = [&]() {
         char *p = (char *)ctx->hPinned;
         double *lam = carve<double>(p, cnt);
         int64_t *sind = carve<int64_t>(p, cnt);
@@ -608,7 +608,44 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
         int64_t tot = 0;
         for (int64_t c = 0; c < cnt; ++c) tot += steps[c];
         ctx->stats.total_steps = tot;
+    };
+    if (early_perk) {
+        AH_CUDA(cudaEventSynchronize(ctx->ev_join));     // recorded on the side stream after the copy of the per-k results
+        unpack();                                        // (the main k_vec is still writing U)
+    } else {
+        AH_CUDA(cudaEventRecord(ctx->ev[6], st));
+        AH_CUDA(cudaMemcpyAsync(ctx->hPinned, ctx->dOut.p, out_bytes(cnt), cudaMemcpyDeviceToHost, st));
+        AH_CUDA(cudaEventRecord(ctx->ev[7], st));
     }
+    AH_CUDA(wait_stream(ctx, st));
+    if (staged) AH_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    const auto t_synced = std::chrono::steady_clock::now();
+    if (!early_perk) unpack();
+    for (int c = 0; c < nchunks; ++c) {   // kernel times of every column block
+        cudaEvent_t *E = &ctx->chunk_ev[5 * (size_t)c];
+        float t = 0.f;
+        AH_CUDA(cudaEventElapsedTime(&t, E[0], E[4]));
+        ms_all += t;
+        if (ctx->mode == 0 && (wantU || wantV)) {
+            AH_CUDA(cudaEventElapsedTime(&t, ctx->side_ev[4 * (size_t)c + 2], ctx->side_ev[4 * (size_t)c + 3]));
+        } else {
+            AH_CUDA(cudaEventElapsedTime(&t, E[3], E[4]));
+        }
+        ctx->stats.full_ms += t;
+        if (ctx->mode == 0) {
+            AH_CUDA(cudaEventElapsedTime(&t, E[0], E[1]));
+            ctx->stats.prep_ms += t;
+            AH_CUDA(cudaEventElapsedTime(&t, E[1], E[2]));
+            ctx->stats.bisect_ms += t;
+            ms_main += t;
+            AH_CUDA(cudaEventElapsedTime(&t, ctx->side_ev[4 * (size_t)c], ctx->side_ev[4 * (size_t)c + 1]));
+            ctx->stats.rem3_ms += t;          // runs beside k_vec: contained in the span below when vectors are wanted
+            ms_main += t;
+            AH_CUDA(cudaEventElapsedTime(&t, E[2], E[3]));
+            ctx->stats.vec_ms += t;
+        }
+    }
+    ctx->stats.d2h_bytes += cnt * (8 * 7 + 4 * 2);
     float th = 0.f, td = 0.f;
     AH_CUDA(cudaEventElapsedTime(&th, ctx->ev[0], ctx->ev[1]));
     AH_CUDA(cudaEventElapsedTime(&td, ctx->ev[6], ctx->ev[7]));

@@ -1270,7 +1270,6 @@ k_rem3_prep(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_
 #pragma unroll
                     for (int u = 0; u < RU; ++u) {
                         if (tile0 + u < ntiles) {
-#pragma unroll
                             static_assert(RH == 2, "tile sum of four terms, as in k_bisect");
                             double t = secular_term_first(dshift<KIND>(dcur[u][0].x, S.sigma), S.x, wcur[u][0].x);
                             t = secular_term_acc(t, dshift<KIND>(dcur[u][0].y, S.sigma), S.x, wcur[u][0].y);
