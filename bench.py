@@ -570,6 +570,22 @@ def _run_ours(args):
                                  "interlacing": bool(np.all(lam[1:] < Pt.D) and np.all(lam[:-1] > Pt.D)),
                                  "trace_rel_err": float(abs(lam.sum() - (Pt.D.sum() + Pt.a)) / np.abs(lam).sum()),
                                  "status_all_ok": bool(((rt.status & 0xff) == 0).all())}}
+            # plain bisection on the same problem (eigenvalues and Info only): bit-identical results, and what it would cost
+            try:
+                os.environ["ARROWHEAD_B200_ACCEL"] = "0"
+                ctx_plain = ab.Context(local_rank)
+                os.environ.pop("ARROWHEAD_B200_ACCEL", None)
+                rp = Pt.solve(ctx_plain, 1, nt, None)
+                torch.cuda.synchronize()
+                target["plain_bisection"] = {"bitwise_identical_lambda_info_status": bool(
+                                                 all(np.array_equal(getattr(rp, f), getattr(rt, f), equal_nan=True)
+                                                     for f in ("lam", "sind", "kb", "kz", "knu", "krho", "qout", "status"))),
+                                             "sweeps_per_eigenpair": float(rp.steps.mean()), "executed_sweeps_per_eigenpair": float(rt.steps.mean()),
+                                             "k_bisect_ms": float(rp.stats["main_kernel_ms"])}
+                ctx_plain.close()
+            except Exception as e:
+                os.environ.pop("ARROWHEAD_B200_ACCEL", None)
+                target["plain_bisection"] = {"error": f"{type(e).__name__}: {e}"[:200]}
             del Ut
         except Exception as e:                                               # never lose the headline line to the sub-record
             target = {"error": f"{type(e).__name__}: {e}"[:200]}
