@@ -152,3 +152,47 @@ def test_accelerated_bisection_fuzz(monkeypatch):
         assert done >= 80
     finally:
         plain.close(); fast.close()
+
+
+@pytest.mark.timeout(900)
+def test_accelerated_bisection_large_structured_families(monkeypatch):
+    """the stress families at n = 12000 (several eigenpairs per slot, time slicing, Remedy-3 round through the ring):
+    eigenvalues, Info, status and the eigenvectors (compared on the device) bit for bit"""
+    import torch
+    plain, fast = _contexts(monkeypatch)
+    try:
+        N = 12000
+        U0 = torch.empty((N + 1, N + 1), dtype=torch.float64, device="cuda")
+        U1 = torch.empty((N + 1, N + 1), dtype=torch.float64, device="cuda")
+        V0 = torch.empty((N + 1, N + 1), dtype=torch.float64, device="cuda")
+        V1 = torch.empty((N + 1, N + 1), dtype=torch.float64, device="cuda")
+
+        def both(call, what, nrows, ncols, v=False):
+            U0.zero_(); U1.zero_()
+            if v: V0.zero_(); V1.zero_()
+            r0 = call(plain, U0, V0); r1 = call(fast, U1, V1)
+            torch.cuda.synchronize()
+            _same(r0, r1, what)
+            assert torch.equal(U0.view(torch.int64), U1.view(torch.int64)), what        # bit patterns (NaN columns of flagged eigenpairs included)
+            if v: assert torch.equal(V0.view(torch.int64), V1.view(torch.int64)), what
+            return int(r0.steps.sum()), int(r1.steps.sum())
+
+        rng = np.random.default_rng(7)
+        s0 = s1 = 0
+        for name, D, z, a in arrow_families(rng, N):
+            if np.any(np.diff(D) >= 0):
+                D = np.unique(D)[::-1].copy(); z = z[:D.size]
+            n = D.size + 1
+            a0, a1 = both(lambda c, U, V: c.symarrow(D, z, a, vectors=False, U_dev=U.data_ptr(), ldu=n), ("symarrow", name), n, n)
+            s0 += a0; s1 += a1
+            rho = abs(a) + 0.1
+            both(lambda c, U, V: c.symdpr1(D, z, rho, vectors=False, U_dev=U.data_ptr(), ldu=D.size), ("symdpr1", name), D.size, D.size)
+        rng = np.random.default_rng(11)
+        for name, D, z in half_families(rng, N - 1):
+            for tip in (1, 0):
+                zz = z if tip else z[:D.size]
+                both(lambda c, U, V: c.halfarrow(D, zz, vectors=False, U_dev=U.data_ptr(), ldu=N + 1, V_dev=V.data_ptr(), ldv=N + 1),
+                     ("halfarrow", name, tip), N + 1, N + 1, v=True)
+        assert s1 < 0.6 * s0
+    finally:
+        plain.close(); fast.close()
