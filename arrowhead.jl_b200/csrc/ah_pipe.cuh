@@ -18,7 +18,12 @@
 // ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier); one tile = 1024 poles.  A CTA bisects BJ = 8 eigenpairs ("slots") at once: each thread moves its 4 poles of the
 // tile from shared memory into registers once and evaluates the term for all 8 slots from there, so
 // L2 and shared-memory traffic per term drop 8x and the FP64 pipe is the only busy unit.  One term is
-// 7 FP64-pipe instructions (DADD d, DFMA e=1-m d, DMUL t=d e, MUFU.RCP64H seed + 3 DFMA, DFMA accumulate).
+// 7.25 FP64-pipe instructions (DADD d, DFMA e=1-m d, DMUL t=d e, MUFU.RCP64H seed + 3 DFMA, DMUL/DFMA into the sum of the
+// tile's 4 terms, one DADD per tile into the running sum).  Most of the reference's ~54 bisection steps are never evaluated:
+// a sweep at any point yields a certified bound for the computed sums at all grid points on one side of it, so the
+// kernel probes near the root (rational model of F), descends the dyadic grid for free wherever a certificate decides,
+// and evaluates only the last few cells, where F is rounding noise -- ~14 sweeps, final bracket bit-identical
+// ("accelerated bisection", see the comment above k_bisect and DESIGN.md section 3).
 // The inner block is branch-free: the one pole per slot that must be skipped (the shift pole, d = 0)
 // poisons that slot's accumulator in exactly one thread, which saves the accumulator before the block
 // and redoes its four terms without the pole afterwards (a rare, warp-divergent side path).
