@@ -207,23 +207,35 @@ k_prep(Problem P, KState *__restrict__ ks, int64_t kbase, int64_t cnt, int64_t *
         if (l0 + 2 * PT < Npi) { d2n = ldg2(D + l0 + 2 * PT); w2n = ldg2(W + l0 + 2 * PT); }   // prefetch the next pair
         const double dv[2] = {d2.x, d2.y};
         const double wv[2] = {w2.x, w2.y};
+        // One thread per eigenpair holds that eigenpair's shift pole (d = 0: not an entry of the inverse), in one iteration.
+        // Every other iteration runs without the per-slot test, so that the 8 independent chains of the pair interleave.
+        bool hit = false;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int l = l0 + h;
+        for (int j = 0; j < PJ; ++j) hit = hit || (l0 == (iis[j] & ~1));
+        auto entry = [&](int h, int j) {
             const double W2 = __dmul_rn(wv[h], wv[h]);
-            if (l < Ni) {
+            const double Dp = rcp_fast(dshift<KIND>(dv[h], sigma[j]));   // feeds sums and maxima over N entries only
+            const double zp = __dmul_rn(__dmul_rn(-wv[h], Dp), wz[j]);
+            const double t = __dmul_rn(W2, Dp);
+            if (Dp > 0.0) a0[j] = __dadd_rn(a0[j], t); else a1[j] = __dadd_rn(a1[j], t);
+            const double az = fabs(zp);
+            a2[j] = __dadd_rn(a2[j], az);
+            a3[j] = fmax(a3[j], __dadd_rn(__dmul_rn(sgn[j], Dp), az));
+            a4[j] = fmax(a4[j], __dadd_rn(fabs(Dp), az));
+        };
+        if (!hit && l0 + 1 < Ni) {
 #pragma unroll
-                for (int j = 0; j < PJ; ++j) {
-                    if (l != iis[j]) {
-                        const double Dp = rcp_fast(dshift<KIND>(dv[h], sigma[j]));   // feeds sums and maxima over N entries only
-                        const double zp = __dmul_rn(__dmul_rn(-wv[h], Dp), wz[j]);
-                        const double t = __dmul_rn(W2, Dp);
-                        if (Dp > 0.0) a0[j] = __dadd_rn(a0[j], t); else a1[j] = __dadd_rn(a1[j], t);
-                        const double az = fabs(zp);
-                        a2[j] = __dadd_rn(a2[j], az);
-                        a3[j] = fmax(a3[j], __dadd_rn(__dmul_rn(sgn[j], Dp), az));
-                        a4[j] = fmax(a4[j], __dadd_rn(fabs(Dp), az));
-                    }
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int j = 0; j < PJ; ++j) entry(h, j);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int l = l0 + h;
+                if (l < Ni) {
+#pragma unroll
+                    for (int j = 0; j < PJ; ++j)
+                        if (l != iis[j]) entry(h, j);
                 }
             }
         }
