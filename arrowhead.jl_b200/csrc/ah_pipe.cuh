@@ -562,7 +562,7 @@ __device__ __forceinline__ void accel_descend(BSlot &S) {
 // value(m) = L(m) + alpha + gamma / (m - q) through the last evaluated points, L(m) = b - m in round 0 (the known linear part
 // of the arrow's secular function), 0 in round 1: with three points q is fitted too (it lumps the poles behind the extreme
 // one), with two q = the extreme pole; if neither lands inside the certified interval, regula falsi on its ends.  The probe
-// sits delta = 1.5 x (certifiable distance) -- 4x more after every probe that could not be certified, never below 4 ulp -- to
+// sits delta = 1.25 x (certifiable distance) -- 4x more after every probe that could not be certified, never below 4 ulp -- to
 // the side of the estimate whose certificate is further away.  Heuristic only: no influence on the result.
 template <int ROUND>
 __device__ __forceinline__ void accel_choose(BSlot &S, double th2) {
@@ -573,8 +573,10 @@ __device__ __forceinline__ void accel_choose(BSlot &S, double th2) {
         const double slope = fabs((F2 - F1) * rcp_fast(x2 - x1));
         const double L1 = (ROUND == 0) ? S.b - x1 : 0.0, L2 = (ROUND == 0) ? S.b - x2 : 0.0;
         const double R1 = F1 - L1, R2 = F2 - L2;
-        const double scale = (ROUND == 0) ? fabs(L2) + fabs(R2) : 1.0 + fabs(sign_jl(S.b) * F2 + 1.0);   // magnitude of the operands of the last addition
-        double delta = 1.5 * th2 * scale * rcp_fast(slope) * (double)(1 << (2 * S.nfail));
+        // the uncertain part of F: wz^2 S (+ the tip term) in round 0, rho S in round 1 -- a point is certifiable once |F| exceeds
+        // th2 times it; 1.25 x that distance (measured on B200: 1.5 x of |b - m| + |R| = 13.7 sweeps per eigenpair, this 12.9)
+        const double scale = (ROUND == 0) ? fabs(R2) : fabs(sign_jl(S.b) * F2 + 1.0);
+        double delta = 1.25 * th2 * scale * rcp_fast(slope) * (double)(1 << (2 * S.nfail));
         delta = fmax(delta, 4.0 * kEps * fabs(x2));
         if (!((b_ - a_) > 6.0 * delta)) S.probing = 0;          // (also when delta is NaN)
         else {

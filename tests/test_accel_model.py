@@ -113,7 +113,7 @@ def accelerated_bisection(I, th2, policy="production", rng=None, audit=False):
                 slope = abs((F2 - F1) / (x2 - x1))
                 L1, L2 = I.b - x1, I.b - x2
                 R1, R2 = F1 - L1, F2 - L2
-                delta = max(1.5 * th2 * (abs(L2) + abs(R2)) / slope * 4.0 ** nfail, 4 * EPS * abs(x2))
+                delta = max(1.25 * th2 * abs(R2) / slope * 4.0 ** nfail, 4 * EPS * abs(x2))
                 if not ((b_ - a_) > 6 * delta):
                     probing = False
                 elif policy == "random":

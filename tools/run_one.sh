@@ -1,0 +1,4 @@
+cd $GRAFT_REPO_ROOT
+timeout 300 python tools/accel_ab.py 2>&1 | grep "accel=1" > gpurun_out/r3m_ab.log
+ARROWHEAD_B200_LIB=$PWD/variants/lib_dfac10.so timeout 300 python tools/accel_ab.py 2>&1 | grep "accel=1" >> gpurun_out/r3m_ab.log
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r3m_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r3m_pytest.log
