@@ -52,6 +52,7 @@ struct ah_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;   // high priority: the short Remedy-3 round runs beside k_vec
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_early0 = nullptr, ev_early1 = nullptr;   // around the early k_full launch on the side stream
     std::vector<cudaEvent_t> side_ev;     // 4 timing events per column block on the side stream (Remedy-3 round, k_full)
     cudaStream_t stream = nullptr;  // the stream kernels run on (own_stream or caller's)
     cudaEvent_t ev[12] = {};
@@ -454,6 +455,24 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             rc = ah::launch_prep(L.kind, P, ks, kb, cc, dlist, dcount, st);
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_prep launch");
             AH_CUDA(cudaEventRecord(E[1], st));
+            // The eigenpairs k_prep hands over (double-double b: K_b / K_z test failed) are latency-bound work for k_full, one
+            // CTA each, ~0.6 ms: they start NOW on the high-priority side stream and run beside k_bisect (whose persistent CTAs
+            // on the few SMs involved simply start taking tickets a little later) instead of after everything else.
+            // dcount[6] = length of the hand-over list at this point; the late k_full launch begins there.
+            AH_CUDA(cudaMemcpyAsync(dcount + 6, dcount, 8, cudaMemcpyDeviceToDevice, st));
+            AH_CUDA(cudaEventRecord(ctx->ev_early0, st));
+            AH_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_early0, 0));
+            {
+                const int grid = (int)std::min<int64_t>(cc, (int64_t)ctx->sm_count);
+                switch (L.kind) {
+                    case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, ctx->side_stream>>>(P, Oc, dlist, kb, 0, dcount + 6); break;
+                    case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, ctx->side_stream>>>(P, Oc, dlist, kb, 0, dcount + 6); break;
+                    default: k_full<KIND_HALF, 256><<<grid, 256, 0, ctx->side_stream>>>(P, Oc, dlist, kb, 0, dcount + 6); break;
+                }
+                AH_CUDA(cudaGetLastError());
+                ctx->stats.launches += 1;
+            }
+            AH_CUDA(cudaEventRecord(ctx->ev_early1, ctx->side_stream));
             if (++ctx->bisect_tag == 0) {   // tags wrapped: forget the old entries
                 AH_CUDA(cudaMemsetAsync(ctx->dQueue.p, 0, ctx->dQueue.cap, st));
                 ctx->bisect_tag = 1;
@@ -494,9 +513,9 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
                     {
                         const int grid = (int)std::min<int64_t>(cc, (int64_t)ctx->sm_count * 4);
                         switch (L.kind) {
-                            case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, rs>>>(P, Oc, dlist, kb, 0, dcount); break;
-                            case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, rs>>>(P, Oc, dlist, kb, 0, dcount); break;
-                            default: k_full<KIND_HALF, 256><<<grid, 256, 0, rs>>>(P, Oc, dlist, kb, 0, dcount); break;
+                            case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, rs>>>(P, Oc, dlist, kb, 0, dcount, dcount + 6); break;
+                            case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, rs>>>(P, Oc, dlist, kb, 0, dcount, dcount + 6); break;
+                            default: k_full<KIND_HALF, 256><<<grid, 256, 0, rs>>>(P, Oc, dlist, kb, 0, dcount, dcount + 6); break;
                         }
                         AH_CUDA(cudaGetLastError());
                         ctx->stats.launches += 1;
@@ -522,11 +541,12 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             if (!side_full) {
                 // the hand-over list is consumed straight from device memory; a few hundred CTAs cover the
                 // ~1 % of eigenpairs that take a Remedy / double-double branch
+                AH_CUDA(cudaStreamWaitEvent(st, ctx->ev_early1, 0));     // (the early k_full of this block, on the side stream)
                 const int grid = (int)std::min<int64_t>(cc, (int64_t)ctx->sm_count * 4);
                 switch (L.kind) {
-                    case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, 0, dcount); break;
-                    case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, 0, dcount); break;
-                    default: k_full<KIND_HALF, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, 0, dcount); break;
+                    case KIND_ARROW: k_full<KIND_ARROW, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, 0, dcount, dcount + 6); break;
+                    case KIND_DPR1: k_full<KIND_DPR1, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, 0, dcount, dcount + 6); break;
+                    default: k_full<KIND_HALF, 256><<<grid, 256, 0, st>>>(P, Oc, dlist, kb, 0, dcount, dcount + 6); break;
                 }
                 AH_CUDA(cudaGetLastError());
                 ctx->stats.launches += 1;
@@ -861,6 +881,8 @@ int ah_create(ah_ctx **pctx, int device) {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
         ok = ok && cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_early0, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_early1, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     }
     for (auto &ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
@@ -896,6 +918,8 @@ void ah_destroy(ah_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_early0) cudaEventDestroy(ctx->ev_early0);
+    if (ctx->ev_early1) cudaEventDestroy(ctx->ev_early1);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (auto &ev : ctx->side_ev) cudaEventDestroy(ev);
     ah_release_nccl(ctx);

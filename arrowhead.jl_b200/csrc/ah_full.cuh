@@ -638,12 +638,16 @@ __device__ void solve_full(const Problem &P, const Outputs &O, int64_t k, int64_
 
 // klist == nullptr: eigenpairs k0 .. k0+nwork-1.  Otherwise the work list written by the fast kernel,
 // whose length is read from *nwork_dev (no host round trip between the two launches).
+// first_dev (optional): the list entries below *first_dev were solved by an earlier launch (the eigenpairs k_prep hands over
+// are started beside k_bisect, those handed over later follow after the Remedy-3 round).
 template <int KIND, int BT>
 __global__ void __launch_bounds__(BT) k_full(Problem P, Outputs O, const int64_t *__restrict__ klist,
-                                             int64_t k0, int64_t nwork, const unsigned long long *nwork_dev) {
+                                             int64_t k0, int64_t nwork, const unsigned long long *nwork_dev,
+                                             const unsigned long long *first_dev = nullptr) {
     __shared__ double red[2 * (BT / 32) + 2];
     if (klist) nwork = (int64_t)*nwork_dev;
-    for (int64_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const int64_t first = first_dev ? (int64_t)*first_dev : 0;
+    for (int64_t wi = first + blockIdx.x; wi < nwork; wi += gridDim.x) {
         const int64_t k = klist ? klist[wi] : k0 + wi;
         solve_full<KIND, BT>(P, O, k, k - k0, red);
     }
