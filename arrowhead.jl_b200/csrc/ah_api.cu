@@ -456,8 +456,9 @@ int run_solver(ah_ctx *ctx, const Launch &L, ah::Problem P, const double *hD, co
             if (rc) return cuda_fail(ctx, (cudaError_t)rc, "k_prep launch");
             AH_CUDA(cudaEventRecord(E[1], st));
             // The eigenpairs k_prep hands over (double-double b: K_b / K_z test failed) are latency-bound work for k_full, one
-            // CTA each, ~0.6 ms: they start NOW on the high-priority side stream and run beside k_bisect (whose persistent CTAs
-            // on the few SMs involved simply start taking tickets a little later) instead of after everything else.
+            // CTA each, ~0.6 ms: they start NOW on the high-priority side stream and run beside k_bisect instead of after
+            // everything else.  k_bisect's grid would fill every SM to the last register, so as many of its CTAs as there are
+            // such eigenpairs (16 at most) return at once and leave their places to k_full's -- only when the list is not empty.
             // dcount[6] = length of the hand-over list at this point; the late k_full launch begins there.
             AH_CUDA(cudaMemcpyAsync(dcount + 6, dcount, 8, cudaMemcpyDeviceToDevice, st));
             AH_CUDA(cudaEventRecord(ctx->ev_early0, st));
