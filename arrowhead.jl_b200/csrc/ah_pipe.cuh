@@ -657,9 +657,9 @@ k_bisect(Problem P, Outputs O, KState *__restrict__ ks, int64_t kbase, int64_t c
          unsigned tag, int quantum, int window, int spec, KExtra *__restrict__ kx, double th2) {
     static_assert(NSLOT >= 1 && NSLOT <= BJ && NSLOT <= BW, "one warp per slot");
     // Round 0: dcount[6] eigenpairs were handed over by k_prep and are being solved by k_full on the side stream, one CTA
-    // each; this grid alone fills every SM, so that many of its CTAs (16 at most, never all) make room.  Work is taken by
-    // ticket, so the others simply do a little more.
-    if (ROUND == 0 && (unsigned long long)blockIdx.x < min(dcount[6], 16ull) && blockIdx.x + 1 < gridDim.x) return;
+    // each; this grid alone fills every SM, so that many of its CTAs (16 at most, and never more than an eighth of the grid)
+    // make room.  Work is taken by ticket, so the others simply do a little more.
+    if (ROUND == 0 && (unsigned long long)blockIdx.x < min(dcount[6], (unsigned long long)min(16u, gridDim.x >> 3))) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BisectShared &sh = *reinterpret_cast<BisectShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
